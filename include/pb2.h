@@ -1,0 +1,201 @@
+/* pb2.h -- C ABI of libpb2 (probability_b200): the B200-native many-chain HMC/NUTS
+ * engine behind the tfp.mcmc hot path.
+ *
+ * The reference (TensorFlow Probability) has NO native/FFI boundary for this path:
+ * it is Python over TF/JAX ops.  The interfaces replaced here are therefore the
+ * reference's Python operator API (paths relative to tensorflow_probability/python/):
+ *
+ *   pb2_rng_*            internal/samplers.py:79-368 (sanitize_seed, fold_in, split_seed,
+ *                        normal, uniform) over jax.random
+ *                        (internal/backend/numpy/random_generators.py:151-158,278-302)
+ *   pb2_logp_grad        mcmc/internal/util.py:286-308 maybe_call_fn_and_grads
+ *   pb2_leapfrog         mcmc/internal/leapfrog_integrator.py:222-316 SimpleLeapfrogIntegrator.__call__
+ *   pb2_run (HMC)        mcmc/hmc.py:501-529,661-729 + mcmc/metropolis_hastings.py:160-254
+ *   pb2_run (NUTS)       mcmc/nuts.py:321-445 NoUTurnSampler.one_step
+ *   pb2_run (n_steps>1)  mcmc/sample.py:81-383 sample_chain (+ internal/loop_util.py:123-253)
+ *   pb2_da_*             mcmc/dual_averaging_step_size_adaptation.py:353-532
+ *   pb2_ess / pb2_rhat   mcmc/diagnostic.py:38-336,339-567
+ *
+ * Conventions: every function returns 0 on success and a negative code on error
+ * (message via pb2_last_error); nothing throws or aborts.  All array arguments named
+ * d_* are DEVICE pointers (float32 / int32 / uint8, row-major, contiguous) owned by
+ * the caller; h_* are HOST pointers.  Work is enqueued on the context's CUDA stream
+ * (pb2_ctx_set_stream) and is asynchronous unless the function returns host values.
+ * One context per (host thread, GPU); calls on one context are not re-entrant.
+ */
+#ifndef PB2_H_
+#define PB2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_VERSION 100
+
+#define PB2_OK 0
+#define PB2_ERR_INVALID (-1)
+#define PB2_ERR_CUDA (-2)
+#define PB2_ERR_UNSUPPORTED (-3)
+
+/* RNG counter layouts (jax_threefry_partitionable True / False). */
+#define PB2_LAYOUT_PARTITIONABLE 0
+#define PB2_LAYOUT_ORIGINAL 1
+
+/* target kinds */
+#define PB2_TARGET_EIGHT_SCHOOLS 0
+#define PB2_TARGET_DENSE_GAUSSIAN 1
+#define PB2_TARGET_LOGISTIC 2
+#define PB2_TARGET_STOCH_VOL 3
+
+/* transition kinds */
+#define PB2_KERNEL_HMC 0
+#define PB2_KERNEL_NUTS 1
+
+/* step size kinds */
+#define PB2_STEP_SCALAR 0
+#define PB2_STEP_PER_DIM 1
+#define PB2_STEP_PER_CHAIN 2
+
+typedef struct pb2_ctx pb2_ctx;
+typedef struct pb2_target pb2_target;
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int pb2_version(void);
+int pb2_ctx_create(int device, pb2_ctx** out);
+int pb2_ctx_destroy(pb2_ctx* ctx);
+int pb2_ctx_set_stream(pb2_ctx* ctx, void* cuda_stream);
+int pb2_ctx_synchronize(pb2_ctx* ctx);
+const char* pb2_last_error(pb2_ctx* ctx); /* ctx may be NULL: last global error */
+/* number of pb2 kernels launched on this context since creation (bench "gpu_launches") */
+long long pb2_launch_count(pb2_ctx* ctx);
+
+/* ---- targets ---------------------------------------------------------------- */
+typedef struct {
+  int kind;       /* PB2_TARGET_* */
+  int dim;        /* state dimension D (eight schools: J+2; logistic: incl. bias; SV: T+3) */
+  int n_rows;     /* logistic: N; stochastic volatility: T; eight schools: J */
+  const float* h_a; /* eight schools: y[J]; dense: precision P[D,D]; logistic: X~[N,D]; SV: returns y[T] */
+  const float* h_b; /* eight schools: sigma[J]; dense: loc[D] or NULL; logistic: labels y[N] (0/1) */
+  float scalar;   /* dense: log-normaliser constant added to the log-prob */
+} pb2_target_desc;
+
+int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* desc, pb2_target** out);
+int pb2_target_destroy(pb2_target* tgt);
+int pb2_target_dim(const pb2_target* tgt);
+
+/* ---- RNG (host-side key algebra; tiny, pure C) --------------------------------- */
+int pb2_rng_split(const uint32_t key[2], int n, int layout, uint32_t* h_out /*[n,2]*/);
+int pb2_rng_fold_in(const uint32_t key[2], uint32_t data, uint32_t out[2]);
+/* ---- RNG (device bulk draws of n elements, flat row-major counters) ------------ */
+int pb2_rng_bits(pb2_ctx* ctx, const uint32_t key[2], long long n, int layout, uint32_t* d_out);
+int pb2_rng_uniform(pb2_ctx* ctx, const uint32_t key[2], long long n, float lo, float hi, int layout,
+                    float* d_out);
+int pb2_rng_normal(pb2_ctx* ctx, const uint32_t key[2], long long n, int layout, float* d_out);
+int pb2_rng_randint(pb2_ctx* ctx, const uint32_t key[2], long long n, int lo, int hi, int layout,
+                    int32_t* d_out);
+
+/* ---- chain layout shared by the calls below ------------------------------------ */
+typedef struct {
+  int B;             /* chains held by this process */
+  int B_global;      /* chains of the whole job (RNG draw shapes use this) */
+  int chain_offset;  /* global index of local chain 0 */
+  int rng_layout;    /* PB2_LAYOUT_* */
+  int n_parts;       /* state parts (one momentum key per part), <= 8 */
+  int part_sizes[8]; /* sizes sum to D */
+} pb2_chain_layout;
+
+/* ---- primitives (parity surface) ----------------------------------------------- */
+int pb2_logp_grad(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x /*[B,D]*/,
+                  float* d_logp /*[B]*/, float* d_grad /*[B,D]*/);
+
+int pb2_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, const float* d_x,
+                 const float* d_logp, const float* d_grad, const float* d_step, int step_kind,
+                 int num_steps, float* d_m_out, float* d_x_out, float* d_logp_out, float* d_grad_out);
+
+/* ---- transitions / sample_chain -------------------------------------------------- */
+typedef struct {
+  int kind;                 /* PB2_KERNEL_HMC | PB2_KERNEL_NUTS */
+  int num_leapfrog_steps;   /* HMC */
+  int max_tree_depth;       /* NUTS (<= 12) */
+  float max_energy_diff;    /* NUTS */
+  int unrolled_leapfrog_steps; /* NUTS */
+  int num_results;          /* R */
+  int num_burnin_steps;
+  int num_steps_between_results;
+  int step_kind;            /* PB2_STEP_* */
+  int explicit_step_seeds;  /* 0: derive per-transition seeds from h_seed (sample_chain);
+                               1: h_step_seeds [n_steps,2] is an INPUT (TransitionKernel.one_step) */
+} pb2_run_cfg;
+
+/* Nullable per-result outputs; leading dimension R = num_results.
+ * Field names follow MetropolisHastingsKernelResults (metropolis_hastings.py:41-56),
+ * UncalibratedHamiltonianMonteCarloKernelResults (hmc.py:40-57) and
+ * NUTSKernelResults (nuts.py:74-91). */
+typedef struct {
+  float* d_states;                    /* [R,B,D] */
+  float* d_target_log_prob;           /* [R,B] */
+  float* d_grads_target_log_prob;     /* [R,B,D] */
+  float* d_log_accept_ratio;          /* [R,B] */
+  uint8_t* d_is_accepted;             /* [R,B] */
+  float* d_step_size;                 /* [R] scalar step size used by the emitting transition */
+  float* d_proposed_state;            /* HMC [R,B,D] */
+  float* d_proposed_target_log_prob;  /* HMC [R,B] */
+  float* d_proposed_grads;            /* HMC [R,B,D] */
+  float* d_log_acceptance_correction; /* HMC [R,B] */
+  float* d_initial_momentum;          /* HMC [R,B,D] */
+  float* d_final_momentum;            /* HMC [R,B,D] */
+  int32_t* d_leapfrogs_taken;         /* NUTS [R,B] */
+  uint8_t* d_has_divergence;          /* NUTS [R,B] */
+  uint8_t* d_reach_max_depth;         /* NUTS [R,B] */
+  float* d_energy;                    /* NUTS [R,B] */
+} pb2_trace;
+
+/* Dual-averaging state (device resident, 16 floats): see pb2_da_init. */
+typedef struct {
+  int enabled;                /* 0: fixed step size */
+  float* d_state;             /* [16] device, from pb2_da_init */
+} pb2_da;
+
+/* Runs num_burnin + 1 + (R-1)*(1+thin) transitions for all B chains, chaining
+ * `step_seed, seed = split(seed)` per transition (sample.py:344-349).  h_seed is
+ * the already-salted seed on entry and the pass-along seed on return; h_step_seeds
+ * (nullable, [n_steps,2]) receives every transition's seed.  d_x/d_logp/d_grad hold
+ * the chain state in and out.  d_step_size: scalar | [D] | [B] per cfg.step_kind; with
+ * dual averaging enabled (scalar only) it is updated in place after every transition
+ * and the reduction over chains is local to this process (single-GPU); multi-GPU
+ * callers run adaptation transitions one at a time and combine pb2_da_partial
+ * results across ranks themselves (see pb2_da_apply).
+ * d_leapfrog_total (nullable, uint64[B]) accumulates gradient evaluations. */
+int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* layout,
+            const pb2_run_cfg* cfg, uint32_t h_seed[2], uint32_t* h_step_seeds, float* d_x,
+            float* d_logp, float* d_grad, float* d_step_size, const pb2_da* da,
+            const pb2_trace* trace, unsigned long long* d_leapfrog_total);
+
+/* ---- dual averaging ---------------------------------------------------------------- */
+/* state layout: [0] error_sum [1] log_averaging_step [2] log_shrinkage_target
+ * [3] step (as float) [4] num_adaptation_steps [5] target_accept_prob
+ * [6] exploration_shrinkage [7] step_count_smoothing [8] decay_rate [9] step_size */
+int pb2_da_init(pb2_ctx* ctx, float step_size, int num_adaptation_steps, float target_accept_prob,
+                float exploration_shrinkage, float step_count_smoothing, float decay_rate,
+                float log_shrinkage_target /* NaN: log(10*step_size) */, int step, float error_sum,
+                float log_averaging_step, float* d_state /*[16]*/);
+/* (max, sum exp(la - max)) of la = min(0, finite_or(-inf)(log_accept_ratio)) over B chains */
+int pb2_da_partial(pb2_ctx* ctx, const float* d_log_accept_ratio, int B, float* d_partial /*[2]*/);
+/* combine n_partials (max,sumexp) pairs, update the state and write the new step size */
+int pb2_da_apply(pb2_ctx* ctx, const float* d_partials /*[n,2]*/, int n_partials, long long B_global,
+                 float* d_state, float* d_step_size_out /* nullable */);
+
+/* ---- diagnostics ------------------------------------------------------------------- */
+/* states [N,B,D] -> ess: cross_chain ? [D] : [B,D].  filter_threshold NaN = None;
+ * filter_beyond_lag < 0 = None. */
+int pb2_ess(pb2_ctx* ctx, const float* d_states, int N, int B, int D, float filter_threshold,
+            int filter_beyond_lag, int filter_beyond_positive_pairs, int cross_chain, float* d_out);
+/* states [N,B,D] -> rhat [D] */
+int pb2_rhat(pb2_ctx* ctx, const float* d_states, int N, int B, int D, int split_chains, float* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB2_H_ */

@@ -1,0 +1,218 @@
+// Persistent chain kernels: one thread group per chain (warp, or whole CTA for the
+// 2519-d stochastic-volatility target), chains pulled from a dynamic queue, each group
+// running transitions [t0,t1) of its chain back to back with the state in registers.
+// sm_100a only.
+#include <algorithm>
+#include "pb2_internal.h"
+
+namespace pb2 {
+
+struct SmemPlan {
+  int cta_floats;    // CTA-shared target data
+  int red_floats;    // block-group reduction buffers
+  int group_floats;  // per-group region (scratch + target + checkpoints)
+  int tgt_off;       // offset of target group smem inside the group region
+  int ck_off;        // offset of checkpoint store inside the group region (-1: global)
+  int ck_floats;     // floats per checkpoint array (m or rho)
+};
+
+template <class Grp, int E, class Tgt, int MODE>
+__global__ void __launch_bounds__(512, 1)
+chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io, const SmemPlan plan) {
+  extern __shared__ __align__(16) float smem[];
+  float* cta = smem;
+  Tgt tgt;
+  tgt.init_cta(tp, cta);
+  __syncthreads();
+  float* gbase;
+  if constexpr (Grp::kIsBlock) gbase = smem + plan.cta_floats + plan.red_floats;
+  else gbase = smem + plan.cta_floats + (threadIdx.x >> 5) * plan.group_floats;
+  auto make_group = [&]() {
+    if constexpr (Grp::kIsBlock) return Grp(gbase, smem + plan.cta_floats);
+    else return Grp(gbase);
+  };
+  Grp grp = make_group();
+  tgt.init_group(tp, grp, cta, gbase + plan.tgt_off);
+  Chain<Grp, E, Tgt> ch(grp, tgt, p);
+  float* ckm = nullptr;
+  float* ckr = nullptr;
+  if constexpr (MODE == kModeNUTS) {
+    if (plan.ck_off >= 0) {
+      ckm = gbase + plan.ck_off;
+    } else {
+      ckm = p.ckpt_global + (size_t)blockIdx.x * 2 * plan.ck_floats;
+    }
+    ckr = ckm + plan.ck_floats;
+  }
+  while (true) {
+    int cc = 0;
+    if (grp.lane == 0) cc = atomicAdd(p.queue, 1);
+    cc = grp.bcast_int(cc, 0);
+    if (cc >= p.B) break;
+    ch.c = cc;
+    ch.cg = (uint64_t)p.chain_offset + (uint64_t)cc;
+    float x[E], g[E], lp;
+    if constexpr (MODE == kModeLogpGrad) {
+      ch.load_vec(io.x_in, x);
+      lp = tgt.logp_grad(grp, x, g);
+      ch.store_vec(io.g_out, 0, g);
+      if (grp.lane == 0) io.lp_out[cc] = lp;
+    } else if constexpr (MODE == kModeLeapfrog) {
+      float m[E], eps[E];
+      ch.load_vec(io.m_in, m);
+      ch.load_vec(io.x_in, x);
+      ch.load_vec(io.g_in, g);
+      lp = io.lp_in[cc];
+      ch.load_eps(0, eps);
+      ch.leapfrog(m, x, lp, g, eps, io.L);
+      ch.store_vec(io.m_out, 0, m);
+      ch.store_vec(io.x_out, 0, x);
+      ch.store_vec(io.g_out, 0, g);
+      if (grp.lane == 0) io.lp_out[cc] = lp;
+    } else {
+      ch.load_vec(p.x, x);
+      ch.load_vec(p.g, g);
+      lp = p.lp[cc];
+      unsigned long long nleap_total = 0;
+#pragma unroll 1
+      for (int t = p.t0; t < p.t1; ++t) {
+        const int r = ch.result_index(t);
+        if constexpr (MODE == kModeHMC) {
+          ch.hmc_transition(t, x, lp, g);
+          nleap_total += (unsigned long long)p.L;
+        } else {
+          typename Chain<Grp, E, Tgt>::NutsOut no;
+          ch.nuts_transition(t, x, lp, g, ckm, ckr, no);
+          nleap_total += (unsigned long long)no.leapfrogs;
+          if (p.lar_last && grp.lane == 0) p.lar_last[cc] = no.log_accept_ratio;
+          if (r >= 0 && grp.lane == 0) {
+            const Trace& tr = p.tr;
+            const size_t o = (size_t)r * p.B + cc;
+            if (tr.log_accept_ratio) tr.log_accept_ratio[o] = no.log_accept_ratio;
+            if (tr.is_accepted) tr.is_accepted[o] = no.accepted ? 1 : 0;
+            if (tr.leapfrogs_taken) tr.leapfrogs_taken[o] = no.leapfrogs;
+            if (tr.has_divergence) tr.has_divergence[o] = no.has_divergence ? 1 : 0;
+            if (tr.reach_max_depth) tr.reach_max_depth[o] = no.reach_max_depth ? 1 : 0;
+            if (tr.energy) tr.energy[o] = no.energy;
+          }
+        }
+        if (r >= 0) {
+          const Trace& tr = p.tr;
+          if (tr.states) ch.store_vec(tr.states, r, x);
+          if (tr.grads) ch.store_vec(tr.grads, r, g);
+          if (grp.lane == 0) {
+            if (tr.target_log_prob) tr.target_log_prob[(size_t)r * p.B + cc] = lp;
+            if (tr.step_size && cc == 0 && p.step_kind == 0)
+              tr.step_size[r] = p.step[(size_t)t * p.step_seq_stride];
+          }
+        }
+      }
+      ch.store_vec(p.x, 0, x);
+      ch.store_vec(p.g, 0, g);
+      if (grp.lane == 0) {
+        p.lp[cc] = lp;
+        if (p.leapfrog_total) p.leapfrog_total[cc] += nleap_total;
+      }
+    }
+  }
+}
+
+template <class Grp, int E, class Tgt, int MODE>
+static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p, const PrimIO& io) {
+  SmemPlan plan{};
+  auto r4 = [](size_t v) { return (int)((v + 3) & ~size_t(3)); };
+  plan.cta_floats = r4(Tgt::cta_smem_floats(tp));
+  plan.red_floats = Grp::kIsBlock ? r4(2 * 8 * (Grp::G / 32)) : 0;
+  plan.tgt_off = 64;
+  int gf = 64 + r4(Tgt::group_smem_floats(tp));
+  plan.ck_floats = 0;
+  plan.ck_off = -1;
+  if (MODE == kModeNUTS) {
+    plan.ck_floats = p.max_depth * E * Grp::G;
+    if (Tgt::kCkptInSmem) {
+      plan.ck_off = gf;
+      gf += 2 * plan.ck_floats;
+    }
+  }
+  plan.group_floats = gf;
+  const size_t cta_bytes = 4ull * (plan.cta_floats + plan.red_floats);
+  const size_t grp_bytes = 4ull * gf;
+  int warps, threads, grid;
+  if (Grp::kIsBlock) {
+    threads = Grp::G;
+    warps = 1;  // groups per CTA
+    grid = std::min(p.B, ctx->num_sms);
+  } else {
+    if (cta_bytes + grp_bytes > (size_t)ctx->max_smem_optin)
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "target data does not fit in shared memory");
+    int wmax = (int)std::min<size_t>(16, (ctx->max_smem_optin - cta_bytes) / grp_bytes);
+    // small batches: spread chains over SMs (latency-bound); big batches: fill each SM
+    int want = (p.B + ctx->num_sms - 1) / ctx->num_sms;
+    warps = std::max(1, std::min(wmax, want));
+    threads = warps * 32;
+    grid = std::min((p.B + warps - 1) / warps, ctx->num_sms);
+  }
+  const size_t smem_bytes = cta_bytes + (size_t)warps * grp_bytes;
+  if (MODE == kModeNUTS && plan.ck_off < 0) {
+    size_t need = (size_t)grid * 2 * plan.ck_floats * sizeof(float);
+    if (need > ctx->ckpt_bytes) {
+      if (ctx->d_ckpt) cudaFree(ctx->d_ckpt);
+      ctx->d_ckpt = nullptr;
+      if (int rc = check_cuda(ctx, cudaMalloc(&ctx->d_ckpt, need), "cudaMalloc(ckpt)")) return rc;
+      ctx->ckpt_bytes = need;
+    }
+    p.ckpt_global = ctx->d_ckpt;
+  }
+  auto kfn = chain_kernel<Grp, E, Tgt, MODE>;
+  if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem_bytes), "cudaFuncSetAttribute"))
+    return rc;
+  if (int rc = check_cuda(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(int), ctx->stream), "memset(queue)"))
+    return rc;
+  p.queue = ctx->d_queue;
+  kfn<<<grid, threads, smem_bytes, ctx->stream>>>(p, tp, io, plan);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "chain_kernel launch");
+}
+
+template <class Grp, int E, class Tgt>
+static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
+  switch (mode) {
+    case kModeLogpGrad: return launch_t<Grp, E, Tgt, kModeLogpGrad>(ctx, tp, p, io);
+    case kModeLeapfrog: return launch_t<Grp, E, Tgt, kModeLeapfrog>(ctx, tp, p, io);
+    case kModeHMC: return launch_t<Grp, E, Tgt, kModeHMC>(ctx, tp, p, io);
+    case kModeNUTS: return launch_t<Grp, E, Tgt, kModeNUTS>(ctx, tp, p, io);
+  }
+  return set_error(ctx, PB2_ERR_INVALID, "bad mode");
+}
+
+int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io) {
+  const int D = tgt->dim;
+  switch (tgt->kind) {
+    case PB2_TARGET_EIGHT_SCHOOLS: {
+      EightSchoolsParams tp{tgt->d_a, tgt->d_b, tgt->n_rows};
+      return launch_mode<WarpG, 1, EightSchoolsT<WarpG, 1>>(ctx, tp, mode, p, io);
+    }
+    case PB2_TARGET_DENSE_GAUSSIAN: {
+      DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, D};
+      if (D <= 32) return launch_mode<WarpG, 1, DenseGaussianT<WarpG, 1>>(ctx, tp, mode, p, io);
+      if (D <= 128) return launch_mode<WarpG, 4, DenseGaussianT<WarpG, 4>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "dense Gaussian: D > 128 not supported");
+    }
+    case PB2_TARGET_LOGISTIC: {
+      LogisticParams tp{tgt->d_a, tgt->d_b, tgt->n_rows, D};
+      if (D <= 8) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 8>>(ctx, tp, mode, p, io);
+      if (D <= 25) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 25>>(ctx, tp, mode, p, io);
+      if (D <= 32) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 32>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "shared-memory logistic: D > 32 (use the row-sharded path)");
+    }
+    case PB2_TARGET_STOCH_VOL: {
+      StochVolParams tp{tgt->d_a, tgt->n_rows};
+      if (D <= 5 * 512) return launch_mode<BlockG<16>, 5, StochVolT<BlockG<16>, 5>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
+    }
+  }
+  return set_error(ctx, PB2_ERR_INVALID, "unknown target kind");
+}
+
+}  // namespace pb2

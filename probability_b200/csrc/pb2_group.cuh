@@ -1,0 +1,89 @@
+// "Group" = the set of threads that cooperatively owns ONE chain.
+//   WarpG      : 32 lanes  (Eight Schools, dense Gaussian, logistic)
+//   BlockG<NW> : a whole CTA of NW warps (stochastic volatility, D = 2519)
+// A chain vector of D floats is held in registers, E per thread, blocked ownership:
+// thread `lane` owns d = lane*E + j, j < E (zero padded past D).  All reductions
+// return the SAME bits to every thread of the group so per-chain control flow
+// (accept / U-turn / divergence) stays uniform inside the group.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pb2 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct WarpG {
+  static constexpr int G = 32;
+  static constexpr bool kIsBlock = false;
+  int lane;
+  float* scratch;  // per-group shared scratch (>= 64 floats), see chain kernels
+  __device__ WarpG(float* s) : lane(threadIdx.x & 31), scratch(s) {}
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ float sum(float v) { return warp_sum(v); }
+  template <int N>
+  __device__ __forceinline__ void sumN(float (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+  }
+  __device__ __forceinline__ int bcast_int(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+};
+
+template <int NW>
+struct BlockG {
+  static constexpr int G = 32 * NW;
+  static constexpr bool kIsBlock = true;
+  static constexpr int kMaxN = 8;
+  int lane;
+  float* scratch;
+  float* red;  // [2][kMaxN][NW] double-buffered partials: one __syncthreads per reduction
+  int parity;
+  __device__ BlockG(float* s, float* r) : lane(threadIdx.x), scratch(s), red(r), parity(0) {}
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  template <int N>
+  __device__ __forceinline__ void sumN(float (&v)[N]) {
+    static_assert(N <= kMaxN, "too many simultaneous reductions");
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    float* buf = red + parity * (kMaxN * NW);
+    parity ^= 1;
+    const int w = lane >> 5;
+    if ((lane & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) buf[i * NW + w] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) s += buf[i * NW + k];
+      v[i] = s;
+    }
+  }
+  __device__ __forceinline__ float sum(float v) {
+    float a[1] = {v};
+    sumN<1>(a);
+    return a[0];
+  }
+  // broadcast through the reduction buffers (value taken from thread `src`)
+  __device__ __forceinline__ float bcast(float v, int src) {
+    float* buf = red + parity * (kMaxN * NW);
+    parity ^= 1;
+    if (lane == src) buf[0] = v;
+    __syncthreads();
+    return buf[0];
+  }
+  __device__ __forceinline__ int bcast_int(int v, int src) {
+    return __float_as_int(bcast(__int_as_float(v), src));
+  }
+};
+
+}  // namespace pb2

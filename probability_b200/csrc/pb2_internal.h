@@ -1,0 +1,81 @@
+// Internal host-side declarations shared by the translation units of libpb2.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "../../include/pb2.h"
+#include "pb2_chain.cuh"
+#include "pb2_targets.cuh"
+
+struct pb2_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int max_smem_optin = 227 * 1024;
+  long long launches = 0;
+  std::string err;
+  int* d_queue = nullptr;          // dynamic chain queue counter
+  float* d_ckpt = nullptr;         // global checkpoint scratch (block-group targets)
+  size_t ckpt_bytes = 0;
+  uint32_t* d_sched = nullptr;     // key schedule scratch
+  size_t sched_bytes = 0;
+  uint32_t* d_step_keys = nullptr;
+  size_t step_keys_bytes = 0;
+  float* d_step_seq = nullptr;     // per-transition scalar step sizes (dual averaging)
+  size_t step_seq_bytes = 0;
+  float* d_partial = nullptr;      // [2] dual-averaging partial
+};
+
+struct pb2_target {
+  pb2_ctx* ctx = nullptr;
+  int kind = 0;
+  int dim = 0;
+  int n_rows = 0;
+  float* d_a = nullptr;
+  float* d_b = nullptr;
+  float scalar = 0.f;
+};
+
+namespace pb2 {
+
+enum Mode : int { kModeLogpGrad = 0, kModeLeapfrog = 1, kModeHMC = 2, kModeNUTS = 3 };
+
+// Extra pointers for the two primitive modes.
+struct PrimIO {
+  const float* m_in;
+  const float* x_in;
+  const float* lp_in;
+  const float* g_in;
+  float* m_out;
+  float* x_out;
+  float* lp_out;
+  float* g_out;
+  int L;
+};
+
+int set_error(pb2_ctx* ctx, int code, const std::string& msg);
+int check_cuda(pb2_ctx* ctx, cudaError_t e, const char* what);
+
+// pb2_chain_kernels.cu
+int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io);
+
+// pb2_misc.cu
+int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);
+int launch_nuts_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int max_depth, int layout,
+                      uint32_t* d_out);
+inline int hmc_sched_stride(int n_parts) { return 2 * (n_parts + 1); }
+inline int nuts_sched_stride(int n_parts, int max_depth) {
+  return 2 * n_parts + 6 * max_depth + 2 * ((1 << max_depth) - 1);
+}
+int launch_da_partial(pb2_ctx* ctx, const float* d_lar, int B, float* d_partial);
+int launch_da_apply(pb2_ctx* ctx, const float* d_partials, int n, long long B_global, float* d_state,
+                    float* d_step_out, float* d_step_seq_next);
+int launch_fill_step_seq(pb2_ctx* ctx, float* d_seq, const float* d_step, int n);
+int launch_rng_fill(pb2_ctx* ctx, Key key, Key key_hi, long long n, int layout, int what, float lo, float hi,
+                    int ilo, int ihi, void* out);
+int launch_ess(pb2_ctx* ctx, const float* d_states, int N, int B, int D, float thr, int use_thr, int max_lag,
+               int pairs, int cross, float* d_mean_scratch, float* d_out);
+int launch_rhat(pb2_ctx* ctx, const float* d_states, int N, int B, int D, int split, float* d_out);
+
+}  // namespace pb2

@@ -1,0 +1,411 @@
+// Fused log-prob + gradient device functions for the four named targets.
+// Each target evaluates (lp, grad) for ONE chain held by a group of threads
+// (see pb2_group.cuh); the closed forms restate
+//   Eight Schools   tfp/mcmc/eight_schools_hmc.py:41-57 (+ normal.py:182-188)
+//   DenseGaussian   inference_gym/targets/ill_conditioned_gaussian.py:77-81,105-106
+//   Logistic        inference_gym/targets/logistic_regression.py:88-103, bernoulli.py:119-135
+//   StochVol        inference_gym/targets/vectorized_stochastic_volatility.py:233-309,346-356
+// with analytic gradients instead of autodiff (tfp/mcmc/internal/util.py:246-308).
+#pragma once
+#include "pb2_group.cuh"
+
+namespace pb2 {
+
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+
+__device__ __forceinline__ float softplusf(float x) {
+  return log1pf(expf(-fabsf(x))) + fmaxf(x, 0.f);
+}
+__device__ __forceinline__ float sigmoidf(float x) {
+  float e = expf(-fabsf(x));
+  float r = 1.0f / (1.0f + e);
+  return x >= 0.f ? r : e * r;
+}
+
+// --------------------------------------------------------------------------
+// Eight Schools (non-centred): x = [mu, tau, z_0..z_{J-1}], J <= 30, E == 1.
+struct EightSchoolsParams {
+  const float* y;      // [J] device
+  const float* sigma;  // [J] device
+  int J;
+};
+
+template <class Grp, int E>
+struct EightSchoolsT {
+  static_assert(E == 1 && !Grp::kIsBlock, "Eight Schools runs warp-per-chain, one element per lane");
+  using Params = EightSchoolsParams;
+  static constexpr bool kCkptInSmem = true;
+  float ys, sig, logsig;
+  bool active;
+  int J;
+  static size_t cta_smem_floats(const Params&) { return 0; }
+  static size_t group_smem_floats(const Params&) { return 0; }
+  __device__ void init_cta(const Params&, float*) {}
+  __device__ void init_group(const Params& p, Grp& grp, float*, float*) {
+    J = p.J;
+    int i = grp.lane - 2;
+    active = (i >= 0 && i < J);
+    sig = active ? p.sigma[i] : 1.f;
+    ys = active ? p.y[i] / sig : 0.f;
+    logsig = active ? logf(sig) : 0.f;
+  }
+  __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
+    const float mu = grp.bcast(x[0], 0);
+    const float tau = grp.bcast(x[0], 1);
+    const float e = expf(tau);
+    const float z = active ? x[0] : 0.f;
+    const float loc = mu + e * z;
+    const float r = active ? (ys - loc / sig) : 0.f;  // normal.py:184-185: x/scale - loc/scale
+    const float w = r / sig;
+    float s[3];
+    s[0] = w;
+    s[1] = w * z;
+    s[2] = active ? ((-0.5f * z * z - kHalfLog2Pi) + (-0.5f * r * r - (kHalfLog2Pi + logsig))) : 0.f;
+    grp.template sumN<3>(s);
+    const float m10 = mu / 10.f;
+    float lp = (-0.5f * m10 * m10 - (kHalfLog2Pi + 2.30258509299404568402f)) +
+               (-0.5f * (tau - 5.f) * (tau - 5.f) - kHalfLog2Pi) + s[2];
+    float gg;
+    if (grp.lane == 0) gg = -mu / 100.f + s[0];
+    else if (grp.lane == 1) gg = -(tau - 5.f) + e * s[1];
+    else gg = active ? (-z + e * w) : 0.f;
+    g[0] = gg;
+    return lp;
+  }
+};
+
+// --------------------------------------------------------------------------
+// Dense Gaussian: lp = -1/2 (x-mu)^T P (x-mu) + c ; g = -P (x-mu).  D <= 32*E.
+struct DenseGaussianParams {
+  const float* P;    // [D, D] device, symmetric
+  const float* loc;  // [D] device
+  float lognorm;
+  int D;
+};
+
+template <class Grp, int E>
+struct DenseGaussianT {
+  static_assert(!Grp::kIsBlock, "dense Gaussian runs warp-per-chain");
+  using Params = DenseGaussianParams;
+  static constexpr bool kCkptInSmem = true;
+  static constexpr int DP = 32 * E;  // padded row length
+  const float* sP;                   // CTA-shared [D][DP]
+  float* xbuf;                       // per-warp [DP]
+  float loc[E];
+  float lognorm;
+  int D;
+  static size_t cta_smem_floats(const Params& p) { return (size_t)p.D * DP; }
+  static size_t group_smem_floats(const Params&) { return DP; }
+  __device__ void init_cta(const Params& p, float* cta) {
+    for (int i = threadIdx.x; i < p.D * DP; i += blockDim.x) {
+      int r = i / DP, c = i - r * DP;
+      cta[i] = (c < p.D) ? p.P[r * p.D + c] : 0.f;
+    }
+  }
+  __device__ void init_group(const Params& p, Grp& grp, float* cta, float* grp_smem) {
+    sP = cta;
+    xbuf = grp_smem;
+    D = p.D;
+    lognorm = p.lognorm;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      int d = grp.lane * E + j;
+      loc[j] = d < D ? p.loc[d] : 0.f;
+    }
+  }
+  __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
+    float xc[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      xc[j] = x[j] - loc[j];
+      xbuf[grp.lane * E + j] = xc[j];
+    }
+    __syncwarp();
+    float acc[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) acc[j] = 0.f;
+    const float* prow = sP + grp.lane * E;
+    if constexpr (E == 4) {
+      // P symmetric: column block of row k == row block; LDS.128 per k, x_k broadcast (LDS.128 per 4 k)
+      const int D4 = D & ~3;
+      for (int k = 0; k < D4; k += 4) {
+        const float4 xk = *reinterpret_cast<const float4*>(xbuf + k);
+        const float4 p0 = *reinterpret_cast<const float4*>(prow + (k + 0) * DP);
+        const float4 p1 = *reinterpret_cast<const float4*>(prow + (k + 1) * DP);
+        const float4 p2 = *reinterpret_cast<const float4*>(prow + (k + 2) * DP);
+        const float4 p3 = *reinterpret_cast<const float4*>(prow + (k + 3) * DP);
+        acc[0] = fmaf(p0.x, xk.x, acc[0]); acc[1] = fmaf(p0.y, xk.x, acc[1]);
+        acc[2] = fmaf(p0.z, xk.x, acc[2]); acc[3] = fmaf(p0.w, xk.x, acc[3]);
+        acc[0] = fmaf(p1.x, xk.y, acc[0]); acc[1] = fmaf(p1.y, xk.y, acc[1]);
+        acc[2] = fmaf(p1.z, xk.y, acc[2]); acc[3] = fmaf(p1.w, xk.y, acc[3]);
+        acc[0] = fmaf(p2.x, xk.z, acc[0]); acc[1] = fmaf(p2.y, xk.z, acc[1]);
+        acc[2] = fmaf(p2.z, xk.z, acc[2]); acc[3] = fmaf(p2.w, xk.z, acc[3]);
+        acc[0] = fmaf(p3.x, xk.w, acc[0]); acc[1] = fmaf(p3.y, xk.w, acc[1]);
+        acc[2] = fmaf(p3.z, xk.w, acc[2]); acc[3] = fmaf(p3.w, xk.w, acc[3]);
+      }
+      for (int k = D4; k < D; ++k) {
+        const float xk = xbuf[k];
+        const float4 p0 = *reinterpret_cast<const float4*>(prow + k * DP);
+        acc[0] = fmaf(p0.x, xk, acc[0]); acc[1] = fmaf(p0.y, xk, acc[1]);
+        acc[2] = fmaf(p0.z, xk, acc[2]); acc[3] = fmaf(p0.w, xk, acc[3]);
+      }
+    } else {
+      for (int k = 0; k < D; ++k) {
+        const float xk = xbuf[k];
+#pragma unroll
+        for (int j = 0; j < E; ++j) acc[j] = fmaf(prow[k * DP + j], xk, acc[j]);
+      }
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      g[j] = -acc[j];
+      part = fmaf(xc[j], g[j], part);
+    }
+    __syncwarp();  // xbuf is rewritten by the next call
+    return fmaf(0.5f, grp.sum(part), lognorm);
+  }
+};
+
+// --------------------------------------------------------------------------
+// Logistic regression, data resident in shared memory: theta on lanes (E == 1,
+// D <= DT <= 32), rows strided over lanes.  X~ already carries the bias column.
+struct LogisticParams {
+  const float* X;  // [N, D] device row-major
+  const float* y;  // [N] device (0/1 as float)
+  int N, D;
+};
+
+template <class Grp, int E, int DT>
+struct LogisticT {
+  static_assert(E == 1 && !Grp::kIsBlock && DT <= 32, "logistic runs warp-per-chain, theta on lanes");
+  using Params = LogisticParams;
+  static constexpr bool kCkptInSmem = true;
+  static constexpr int RS = DT | 1;  // odd row stride: conflict-free when lanes walk rows
+  const float* sX;
+  const float* sy;
+  int N, D;
+  static size_t cta_smem_floats(const Params& p) { return (size_t)p.N * RS + p.N; }
+  static size_t group_smem_floats(const Params&) { return 0; }
+  __device__ void init_cta(const Params& p, float* cta) {
+    for (int i = threadIdx.x; i < p.N * RS; i += blockDim.x) {
+      int r = i / RS, c = i - r * RS;
+      cta[i] = (c < p.D) ? p.X[r * p.D + c] : 0.f;
+    }
+    float* yy = cta + (size_t)p.N * RS;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) yy[i] = p.y[i];
+  }
+  __device__ void init_group(const Params& p, Grp&, float* cta, float*) {
+    sX = cta;
+    sy = cta + (size_t)p.N * RS;
+    N = p.N;
+    D = p.D;
+  }
+  __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
+    float th[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) th[d] = __shfl_sync(0xffffffffu, x[0], d);  // lanes >= D hold 0
+    float acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    float ll = 0.f;
+    for (int n = grp.lane; n < N; n += 32) {
+      const float* row = sX + n * RS;
+      float xr[DT];
+      float z = 0.f;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        xr[d] = row[d];
+        z = fmaf(xr[d], th[d], z);
+      }
+      const float yn = sy[n];
+      const float e = __expf(-fabsf(z));
+      const float r = __fdividef(1.0f, 1.0f + e);
+      const float sg = z >= 0.f ? r : e * r;
+      ll += yn * z - (__logf(1.0f + e) + fmaxf(z, 0.f));
+      const float w = yn - sg;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) acc[d] = fmaf(xr[d], w, acc[d]);
+    }
+    // transpose-reduce: 31 shuffles leave the total of index l on lane l
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const bool up = (grp.lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float send = up ? acc[i] : acc[i + o];
+        const float keep = up ? acc[i + o] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    const float th_own = x[0];
+    const bool own = grp.lane < D;
+    g[0] = own ? (-th_own + acc[0]) : 0.f;
+    float part = ll + (own ? (-0.5f * th_own * th_own - kHalfLog2Pi) : 0.f);
+    return grp.sum(part);
+  }
+};
+
+// --------------------------------------------------------------------------
+// Stochastic volatility (non-centred, unconstrained space): u = [u_phi, m, u_s, z_0..z_{T-1}].
+// One CTA per chain; thread `lane` owns d = lane*E + j (time index tau = d - 3), so the
+// AR(1) recurrence h_t = phi h_{t-1} + s z_t and its adjoint lambda_t = a_t + phi lambda_{t+1}
+// are block-wide scans of affine maps (thread-serial, warp Kogge-Stone, cross-warp via smem).
+struct StochVolParams {
+  const float* y;  // [T] device, centred returns
+  int T;
+};
+
+template <class Grp, int E>
+struct StochVolT {
+  static_assert(Grp::kIsBlock && E >= 4, "stochastic volatility runs CTA-per-chain");
+  using Params = StochVolParams;
+  static constexpr bool kCkptInSmem = false;
+  static constexpr int NW = Grp::G / 32;
+  float ysq[E];
+  int T;
+  float* prm;  // [8] phi, m, s, rs, lp_params
+  float* wtf;  // [2*NW] forward warp totals (A,B)
+  float* wtr;  // [2*NW] reverse warp totals
+  static size_t cta_smem_floats(const Params&) { return 0; }
+  static size_t group_smem_floats(const Params&) { return 8 + 4 * NW; }
+  __device__ void init_cta(const Params&, float*) {}
+  __device__ void init_group(const Params& p, Grp& grp, float*, float* gs) {
+    T = p.T;
+    prm = gs;
+    wtf = gs + 8;
+    wtr = gs + 8 + 2 * NW;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      int tau = grp.lane * E + j - 3;
+      float yv = (tau >= 0 && tau < T) ? p.y[tau] : 0.f;
+      ysq[j] = yv * yv;
+    }
+  }
+  __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
+    const int lane = grp.lane, wl = lane & 31, w = lane >> 5;
+    float sg = 0.f, sgm = 0.f, sg3 = 0.f, sgm3 = 0.f;
+    if (lane == 0) {
+      const float u1 = x[0], mm = x[1], u3 = x[2];
+      sg = sigmoidf(u1); sgm = sigmoidf(-u1);
+      sg3 = sigmoidf(u3); sgm3 = sigmoidf(-u3);
+      const float phi0 = 2.f * sg - 1.f;
+      const float s0 = softplusf(u3);
+      const float rs0 = 1.0f / sqrtf(1.f - phi0 * phi0);
+      const float b = (phi0 + 1.f) * 0.5f;
+      // Beta(20,1.5).log_prob(b) - log 2 ; lbeta(20,1.5) = lgamma(20)+lgamma(1.5)-lgamma(21.5)
+      const float lp_phi = 19.f * logf(b) + 0.5f * log1pf(-b) - (-4.63282391111f) - 0.693147180559945f;
+      const float m5 = mm / 5.f;
+      const float lp_m = -2.75416779828f - log1pf(m5 * m5);           // -log(pi*5)
+      const float s2 = s0 * 0.5f;
+      const float lp_s = 0.693147180559945f - 1.83787706640935f - log1pf(s2 * s2);  // log2 - log(2 pi)
+      const float fldj = (0.693147180559945f - softplusf(-u1) - softplusf(u1)) + (-softplusf(-u3));
+      prm[0] = phi0; prm[1] = mm; prm[2] = s0; prm[3] = rs0;
+      prm[4] = lp_phi + lp_m + lp_s + fldj;
+    }
+    __syncthreads();
+    const float phi = prm[0], m = prm[1], s = prm[2], rs = prm[3], lp_params = prm[4];
+    // ---- forward scan: h
+    float A = 1.f, Bc = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int tau = lane * E + j - 3;
+      if (tau >= 0 && tau < T) {
+        const float b = (tau == 0) ? s * x[j] * rs : s * x[j];
+        Bc = fmaf(phi, Bc, b);
+        A *= phi;
+      }
+    }
+    float Ai = A, Bi = Bc;  // inclusive within warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float Ap = __shfl_up_sync(0xffffffffu, Ai, o);
+      const float Bp = __shfl_up_sync(0xffffffffu, Bi, o);
+      if (wl >= o) { Bi = fmaf(Ai, Bp, Bi); Ai *= Ap; }
+    }
+    if (wl == 31) { wtf[2 * w] = Ai; wtf[2 * w + 1] = Bi; }
+    float Bex = __shfl_up_sync(0xffffffffu, Bi, 1);
+    float Aex = __shfl_up_sync(0xffffffffu, Ai, 1);
+    if (wl == 0) { Bex = 0.f; Aex = 1.f; }
+    __syncthreads();
+    float hw = 0.f;  // h entering this warp
+    for (int k = 0; k < w; ++k) hw = fmaf(wtf[2 * k], hw, wtf[2 * k + 1]);
+    const float hin = fmaf(Aex, hw, Bex);
+    float h[E], a[E];
+    float hcur = hin;
+    float s_a = 0.f, s_lik = 0.f, s_z = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int tau = lane * E + j - 3;
+      h[j] = hcur;  // h_{tau-1}
+      a[j] = 0.f;
+      if (tau >= 0 && tau < T) {
+        const float b = (tau == 0) ? s * x[j] * rs : s * x[j];
+        hcur = fmaf(phi, hcur, b);
+        const float hm = hcur + m;
+        const float y2e = ysq[j] * expf(-hm);
+        a[j] = 0.5f * (y2e - 1.f);
+        s_a += a[j];
+        s_lik += -0.5f * y2e - kHalfLog2Pi - 0.5f * hm;
+        s_z += -0.5f * x[j] * x[j] - kHalfLog2Pi;
+      }
+    }
+    // ---- reverse scan: lambda_tau = a_tau + phi * lambda_{tau+1}
+    float Ar = 1.f, Br = 0.f;
+#pragma unroll
+    for (int j = E - 1; j >= 0; --j) {
+      const int tau = lane * E + j - 3;
+      if (tau >= 0 && tau < T) { Br = fmaf(phi, Br, a[j]); Ar *= phi; }
+    }
+    float Ari = Ar, Bri = Br;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float Ap = __shfl_down_sync(0xffffffffu, Ari, o);
+      const float Bp = __shfl_down_sync(0xffffffffu, Bri, o);
+      if (wl + o < 32) { Bri = fmaf(Ari, Bp, Bri); Ari *= Ap; }
+    }
+    if (wl == 0) { wtr[2 * w] = Ari; wtr[2 * w + 1] = Bri; }
+    float Brex = __shfl_down_sync(0xffffffffu, Bri, 1);
+    float Arex = __shfl_down_sync(0xffffffffu, Ari, 1);
+    if (wl == 31) { Brex = 0.f; Arex = 1.f; }
+    __syncthreads();
+    float lw = 0.f;  // lambda entering this warp from the right
+    for (int k = NW - 1; k > w; --k) lw = fmaf(wtr[2 * k], lw, wtr[2 * k + 1]);
+    float lam = fmaf(Arex, lw, Brex);
+    float s_lc = 0.f, s_lh = 0.f;
+    float lam0 = 0.f, z0 = 0.f;
+#pragma unroll
+    for (int j = E - 1; j >= 0; --j) {
+      const int tau = lane * E + j - 3;
+      float gg = 0.f;
+      if (tau >= 0 && tau < T) {
+        lam = fmaf(phi, lam, a[j]);
+        if (tau == 0) {
+          s_lc = fmaf(lam, x[j] * rs, s_lc);
+          gg = s * lam * rs - x[j];
+          lam0 = lam; z0 = x[j];
+        } else {
+          s_lc = fmaf(lam, x[j], s_lc);
+          s_lh = fmaf(lam, h[j], s_lh);
+          gg = fmaf(s, lam, -x[j]);
+        }
+      }
+      g[j] = gg;
+    }
+    float sums[5] = {s_a, s_lik, s_z, s_lc, s_lh};
+    grp.template sumN<5>(sums);
+    if (lane == 0) {
+      const float b = (phi + 1.f) * 0.5f;
+      const float m5 = m / 5.f, s2 = s * 0.5f;
+      const float d_m = sums[0] - (2.f * m / 25.f) / (1.f + m5 * m5);
+      const float d_s = sums[3] - s2 / (1.f + s2 * s2);
+      const float d_phi = sums[4] + lam0 * s * z0 * phi * rs * rs * rs + 0.5f * (19.f / b - 0.5f / (1.f - b));
+      g[0] = d_phi * (2.f * sg * sgm) + (sgm - sg);
+      g[1] = d_m;
+      g[2] = d_s * sg3 + sgm3;
+    }
+    return sums[1] + sums[2] + lp_params;
+  }
+};
+
+}  // namespace pb2

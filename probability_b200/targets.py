@@ -1,0 +1,176 @@
+"""Named target densities with fused log-prob + gradient CUDA kernels.
+
+A target object plays the role of the reference's `target_log_prob_fn` callable
+(hmc.py:413-415): calling it with the state parts returns the per-chain log-prob.
+Because the transition kernels are persistent CUDA kernels, an arbitrary Python
+callable cannot be used; the kernels accept these target objects only and raise
+otherwise (no CPU / autodiff fallback).
+
+  EightSchools            tfp/mcmc/eight_schools_hmc.py:41-76
+  DenseGaussian           MVNTriL log_prob; IllConditionedGaussian =
+                          inference_gym/targets/ill_conditioned_gaussian.py:30-110
+  LogisticRegression      inference_gym/targets/logistic_regression.py:42-171
+  StochasticVolatility    inference_gym/targets/vectorized_stochastic_volatility.py:102-440
+                          (non-centred, unconstrained space; `constrain` maps back)
+"""
+import ctypes as C
+
+import numpy as np
+
+from probability_b200 import _lib
+
+
+class Target:
+  """Base: owns a pb2_target handle per device, created lazily."""
+  kind = None
+
+  def __init__(self, dim, n_rows, a, b=None, scalar=0.0, part_sizes=None):
+    self.dim = int(dim)
+    self.n_rows = int(n_rows)
+    self._a = np.ascontiguousarray(a, np.float32)
+    self._b = None if b is None else np.ascontiguousarray(b, np.float32)
+    self._scalar = float(scalar)
+    self.part_sizes = list(part_sizes) if part_sizes is not None else [self.dim]
+    self._handles = {}
+
+  def handle(self, ctx):
+    h = self._handles.get(ctx.device_index)
+    if h is None:
+      desc = _lib.TargetDesc(
+          kind=self.kind, dim=self.dim, n_rows=self.n_rows,
+          h_a=self._a.ctypes.data_as(_lib.c_f32p),
+          h_b=(self._b.ctypes.data_as(_lib.c_f32p) if self._b is not None else None),
+          scalar=self._scalar)
+      h = C.c_void_p()
+      _lib.check(ctx.lib.pb2_target_create(ctx.handle, C.byref(desc), C.byref(h)), ctx.handle)
+      self._handles[ctx.device_index] = h
+    return h
+
+  # -- the `target_log_prob_fn` protocol ------------------------------------
+  def log_prob_and_grad(self, x):
+    """x: float32 CUDA tensor [B, D] -> (lp [B], grad [B, D])  (mcmc/internal/util.py:286-308)."""
+    import torch
+    if x.dim() != 2 or x.shape[1] != self.dim:
+      raise ValueError('expected state of shape [chains, {}], got {}'.format(self.dim, tuple(x.shape)))
+    x = x.contiguous().float()
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    lp = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    g = torch.empty_like(x)
+    _lib.check(ctx.lib.pb2_logp_grad(ctx.handle, self.handle(ctx), x.shape[0], _lib.ptr(x), _lib.ptr(lp),
+                                     _lib.ptr(g)), ctx.handle)
+    return lp, g
+
+  def __call__(self, *state_parts):
+    from probability_b200.mcmc import _engine
+    x, _, _ = _engine.flatten_state(list(state_parts))
+    return self.log_prob_and_grad(x)[0]
+
+
+class EightSchools(Target):
+  kind = _lib.TARGET_EIGHT_SCHOOLS
+  TREATMENT_EFFECTS = [28, 8, -3, 7, -1, 1, 18, 12]      # eight_schools_hmc.py:69-72
+  TREATMENT_STDDEVS = [15, 10, 16, 11, 9, 11, 10, 18]    # :73-76
+
+  def __init__(self, treatment_effects=None, treatment_stddevs=None):
+    y = self.TREATMENT_EFFECTS if treatment_effects is None else treatment_effects
+    s = self.TREATMENT_STDDEVS if treatment_stddevs is None else treatment_stddevs
+    y = np.asarray(y, np.float32)
+    s = np.asarray(s, np.float32)
+    if y.shape != s.shape or y.ndim != 1:
+      raise ValueError('treatment_effects and treatment_stddevs must be 1-d and equal length')
+    super().__init__(dim=y.size + 2, n_rows=y.size, a=y, b=s, part_sizes=[1, 1, y.size])
+
+
+class DenseGaussian(Target):
+  """N(loc, covariance) evaluated as -1/2 (x-loc)^T P (x-loc) + const with a fixed fp32
+  precision matrix P (cholesky of float32(cov), inverted in float64)."""
+  kind = _lib.TARGET_DENSE_GAUSSIAN
+
+  def __init__(self, covariance=None, loc=None, precision=None, log_normalizer=None):
+    if precision is None:
+      cov32 = np.asarray(covariance, np.float32)
+      L = np.linalg.cholesky(cov32.astype(np.float64)).astype(np.float32).astype(np.float64)
+      P = np.linalg.inv(L @ L.T)
+      P = 0.5 * (P + P.T)
+      const = -np.sum(np.log(np.diag(L))) - 0.5 * cov32.shape[0] * np.log(2 * np.pi)
+    else:
+      P = np.asarray(precision, np.float64)
+      const = 0.0 if log_normalizer is None else log_normalizer
+    self.precision = P.astype(np.float32)
+    self.log_normalizer = float(const)
+    d = P.shape[0]
+    self.loc = np.zeros(d, np.float32) if loc is None else np.asarray(loc, np.float32)
+    super().__init__(dim=d, n_rows=d, a=self.precision, b=self.loc, scalar=const)
+
+
+class IllConditionedGaussian(DenseGaussian):
+  def __init__(self, ndims=100, gamma_shape_parameter=0.5, max_eigvalue=None, seed=10):
+    rng = np.random.RandomState(seed=seed & (2**32 - 1))
+    eigenvalues = 1. / np.sort(rng.gamma(shape=gamma_shape_parameter, scale=1., size=ndims))
+    if max_eigvalue is not None:
+      eigenvalues *= max_eigvalue / eigenvalues.max()
+    q, r = np.linalg.qr(rng.randn(ndims, ndims))
+    q *= np.sign(np.diag(r))
+    self.covariance = (q * eigenvalues).dot(q.T)
+    self.covariance_eigenvalues = eigenvalues
+    super().__init__(covariance=self.covariance)
+
+
+class LogisticRegression(Target):
+  """weights ~ N(0, I); labels ~ Bernoulli(logits = [features, 1] @ weights)."""
+  kind = _lib.TARGET_LOGISTIC
+
+  def __init__(self, train_features, train_labels):
+    X = np.asarray(train_features, np.float32)
+    X = np.concatenate([X, np.ones([X.shape[0], 1], np.float32)], axis=-1)   # logistic_regression.py:36-39
+    y = np.asarray(train_labels).astype(np.float32)
+    if y.shape != (X.shape[0],):
+      raise ValueError('train_labels must have shape [num_train_points]')
+    self.features_with_bias = X
+    self.labels = y
+    super().__init__(dim=X.shape[1], n_rows=X.shape[0], a=X, b=y)
+
+
+class StochasticVolatility(Target):
+  """State (unconstrained): [logit-ish persistence, mean_log_volatility, softplus^-1 shock scale,
+  std_log_volatility[T]]."""
+  kind = _lib.TARGET_STOCH_VOL
+
+  def __init__(self, centered_returns):
+    y = np.asarray(centered_returns, np.float32)
+    self.centered_returns = y
+    super().__init__(dim=y.size + 3, n_rows=y.size, a=y, part_sizes=[1, 1, 1, y.size])
+
+  @staticmethod
+  def constrain(u):
+    """default_event_space_bijector forward (vectorized_stochastic_volatility.py:346-356):
+    Sigmoid(-1, 1), Identity, Softplus, Identity -- elementwise torch ops on the result."""
+    import torch
+    out = u.clone()
+    out[..., 0] = 2.0 * torch.sigmoid(u[..., 0]) - 1.0
+    out[..., 2] = torch.nn.functional.softplus(u[..., 2])
+    return out
+
+
+def synthetic_sv_returns(T=2516, phi=0.95, s=0.25, m=None, seed=0):
+  rng = np.random.default_rng(seed)
+  m = 2.0 * np.log(15.0) if m is None else m
+  h = np.empty(T)
+  h[0] = s * rng.standard_normal() / np.sqrt(1 - phi * phi)
+  for t in range(1, T):
+    h[t] = phi * h[t - 1] + s * rng.standard_normal()
+  y = rng.standard_normal(T) * np.exp(0.5 * (h + m))
+  return (y - y.mean()).astype(np.float32)
+
+
+def synthetic_logistic_data(n=1000, d=24, seed=0):
+  """Features WITHOUT the bias column (LogisticRegression adds it) and 0/1 labels."""
+  rng = np.random.default_rng(seed)
+  X = rng.standard_normal((n, d))
+  X = (X - X.mean(0)) / X.std(0)
+  Xb = np.concatenate([X, np.ones((n, 1))], axis=1)
+  theta = rng.standard_normal(d + 1)
+  p = 1.0 / (1.0 + np.exp(-(Xb @ theta)))
+  y = (rng.random(n) < p).astype(np.float32)
+  return X.astype(np.float32), y

@@ -1,0 +1,19 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: test needs a CUDA device (B200)')
+
+
+@pytest.fixture(scope='session')
+def lib_built():
+  """libpb2.so must exist (nvcc cross-compiles without a GPU)."""
+  from probability_b200 import build
+  return build.build()
