@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the many-chain NUTS hot path (BASELINE.json).
+
+Workload (N=1): configs[1] of BASELINE.json -- ill-conditioned dense Gaussian, 100-d, NUTS
+(max_tree_depth 10) over 16,384 chains per GPU; chains start from exact target draws, the
+step size comes from an untimed dual-averaging warm-up.  A "step" is one NUTS transition of
+every chain.  metric = leapfrog gradient evaluations per second (sum of leapfrogs_taken over
+chains and timed transitions / device time, max over ranks).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, libpb2)
+  python bench.py --impl reference [...]                        CPU arm: the oracle port of the
+                                                                TFP algorithm on the host cores
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'leapfrog_grad_evals_per_sec'
+UNIT = 'grad-evals/s'
+D = 100
+MAX_DEPTH = 10
+CHAINS_PER_GPU = 16384
+ADAPT_STEPS = 150
+EPS0 = 0.158          # 0.5 * D**-0.25 (windowed_sampling.py:566-589)
+
+
+def log(*a):
+  print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return d, 'measured'
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+def exact_draws(cov, n, seed):
+  rng = np.random.default_rng(seed)
+  L = np.linalg.cholesky(cov)
+  return (rng.standard_normal((n, cov.shape[0])) @ L.T).astype(np.float32)
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons DURING the timed region."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.proc = None
+    self.lines = []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.th = threading.Thread(target=self._read, daemon=True)
+      self.th.start()
+    except Exception:  # pylint: disable=broad-except
+      self.proc = None
+
+  def _read(self):
+    for ln in self.proc.stdout:
+      self.lines.append(ln.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm, mx, reasons = [], [], set()
+    for ln in self.lines:
+      f = [x.strip() for x in ln.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(name)
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_reference_arm(steps, warmup, budget_s=25.0):
+  """The oracle port (lock-step batched NumPy restatement of nuts.py) on the host cores."""
+  from oracle import mcmc as omcmc
+  from oracle import rng as orng
+  from oracle import targets as otargets
+  cov, _ = otargets.ill_conditioned_covariance(D)
+  P, c = otargets.gaussian_precision_from_cov(cov)
+  tgt = otargets.DenseGaussian(P, c)
+  B = 1024
+  x = exact_draws(cov, B, seed=123)
+  lp, g = tgt.logp_grad(x)
+  eps = np.float32(0.7)   # close to what dual averaging finds on the GPU arm
+  seed = orng.sanitize_seed(17, salt='mcmc.sample_chain')
+  for _ in range(max(1, min(warmup, 1))):
+    s, seed = orng.split(seed, 2)
+    r = omcmc.nuts_one_step(tgt, x, lp, g, eps, s, max_tree_depth=MAX_DEPTH)
+    x, lp, g = r['state'], r['target_log_prob'], r['grads']
+  t0 = time.perf_counter()
+  n_grad = 0
+  done = 0
+  while done < max(1, steps) and (time.perf_counter() - t0) < budget_s:
+    s, seed = orng.split(seed, 2)
+    r = omcmc.nuts_one_step(tgt, x, lp, g, eps, s, max_tree_depth=MAX_DEPTH)
+    x, lp, g = r['state'], r['target_log_prob'], r['grads']
+    n_grad += int(r['leapfrogs_taken'].sum())
+    done += 1
+  dt = time.perf_counter() - t0
+  return {'value': n_grad / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+          'sample': '%d chains x %d NUTS transitions (depth<=%d, eps=%.2f), NumPy float32 lock-step port of '
+                    'tfp nuts.py, BLAS threads = all cores; %.1fs' % (B, done, MAX_DEPTH, eps, dt)}, done, dt
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours')
+  ap.add_argument('--chains', type=int, default=CHAINS_PER_GPU)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-ess', action='store_true')
+  ap.add_argument('--step-size', type=float, default=None, help='skip dual averaging (profiling runs)')
+  args = ap.parse_args()
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  config = {'workload': 'ill-conditioned dense Gaussian 100-d (inference_gym seed 10), NUTS max_tree_depth=10, '
+                        '%d chains per GPU' % args.chains,
+            'chains_per_gpu': args.chains, 'chains_total': args.chains * max(world, 1), 'dim': D,
+            'max_tree_depth': MAX_DEPTH, 'parallelism': 'chains sharded, no data-path collective',
+            'l2': 'flushed (256 MiB write) between timed transitions',
+            'init': 'exact target draws; step size from %d untimed dual-averaging steps' % ADAPT_STEPS}
+
+  if args.impl == 'reference':
+    if rank != 0:
+      return
+    cb, done, dt = cpu_reference_arm(args.steps, args.warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': done, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / max(done, 1),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': config, 'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return
+
+  import torch
+  import torch.distributed as dist
+  import probability_b200 as tfp
+  from probability_b200 import _lib
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (B200); there is no CPU fallback for the product path.')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  B = args.chains
+  shard = tfp.mcmc.ChainShard(chain_offset=rank * B, num_chains_global=world * B)
+  target = tfp.targets.IllConditionedGaussian(ndims=D)
+  x_host = exact_draws(target.covariance, world * B, seed=123)[rank * B:(rank + 1) * B]
+  x_pinned = torch.from_numpy(np.ascontiguousarray(x_host)).pin_memory()
+  state = x_pinned.to(dev, non_blocking=True)
+  ctx = _lib.Context.get(dev)
+
+  # ---- untimed: dual-averaging warm-up (cross-rank log-mean-exp when sharded)
+  nuts = tfp.mcmc.NoUTurnSampler(target, step_size=EPS0, max_tree_depth=MAX_DEPTH, experimental_chain_shard=shard)
+  da = tfp.mcmc.DualAveragingStepSizeAdaptation(
+      nuts, num_adaptation_steps=ADAPT_STEPS,
+      experimental_reduce_chain_axis_names='ranks' if world > 1 else None)
+  t0 = time.perf_counter()
+  if args.step_size is None:
+    res = tfp.mcmc.sample_chain(1, state, kernel=da, num_burnin_steps=ADAPT_STEPS, trace_fn=None, seed=17,
+                                return_final_kernel_results=True)
+    torch.cuda.synchronize()
+    eps = float(res.final_kernel_results.new_step_size)
+    state = res.all_states[0].contiguous()
+  else:  # profiling runs: skip the adaptation launches
+    eps = args.step_size
+  log('[rank %d] warm-up %.2fs, adapted step size %.4f' % (rank, time.perf_counter() - t0, eps))
+  nuts = nuts.copy(step_size=eps)
+  pkr = nuts.bootstrap_results(state)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  seed = tfp.random.sanitize_seed(18, salt='mcmc.sample_chain')
+
+  def one_transition(st, kr, sd):
+    step_seed, sd = tfp.random.split_seed(sd)
+    st, kr = nuts.one_step(st, kr, seed=step_seed)
+    return st, kr, sd
+
+  for _ in range(max(args.warmup, 3)):
+    state, pkr, seed = one_transition(state, pkr, seed)
+  torch.cuda.synchronize()
+
+  # ---- timed region: K transitions, L2 flushed between them, CUDA events on the launch stream
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  launches0 = ctx.launch_count()
+  evs = []
+  leap = []
+  for _ in range(args.steps):
+    flush.fill_(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    state, pkr, seed = one_transition(state, pkr, seed)
+    e1.record()
+    evs.append((e0, e1))
+    leap.append(pkr.leapfrogs_taken)
+  torch.cuda.synchronize()
+  launches = ctx.launch_count() - launches0
+  clocks = sampler.stop()
+  if world > 1:
+    dist.barrier()
+  step_ms = [a.elapsed_time(b) for a, b in evs]
+  total_s = sum(step_ms) / 1e3
+  n_grad = float(sum(int(l.sum().item()) for l in leap))
+  tt = torch.tensor([total_s], device=dev, dtype=torch.float64)
+  ng = torch.tensor([n_grad], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ng, op=dist.ReduceOp.SUM)
+  total_s = float(tt.item())
+  n_grad_all = float(ng.item())
+  value = n_grad_all / total_s
+
+  # ---- persistent (fused) run of the same K transitions: one launch, state on-chip throughout
+  tot = torch.zeros(B, dtype=torch.int64, device=dev)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  e0.record()
+  tfp.mcmc.sample_chain(args.steps, state, kernel=nuts, previous_kernel_results=pkr, trace_fn=None, seed=19,
+                        experimental_leapfrog_total=tot)
+  e1.record()
+  torch.cuda.synchronize()
+  fused_s = e0.elapsed_time(e1) / 1e3
+  fused = torch.tensor([float(tot.sum().item()), fused_s], device=dev, dtype=torch.float64)
+  if world > 1:
+    g = [torch.zeros_like(fused) for _ in range(world)]
+    dist.all_gather(g, fused)
+    fused_value = sum(float(v[0]) for v in g) / max(float(v[1]) for v in g)
+  else:
+    fused_value = float(fused[0]) / float(fused[1])
+
+  # ---- e2e: the public API with HOST buffers, per step: H2D state, sample_chain(1), D2H state + counts
+  out_pinned = torch.empty(B, D, dtype=torch.float32).pin_memory()
+  cnt_pinned = torch.empty(B, dtype=torch.int32).pin_memory()
+  x_pinned.copy_(state.cpu())
+  e2e_steps = max(3, min(args.steps, 10))
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  e2e_grad = 0
+  for i in range(e2e_steps):
+    st = x_pinned.to(dev, non_blocking=True)
+    r = tfp.mcmc.sample_chain(1, st, kernel=nuts, trace_fn=lambda _, kr: kr.leapfrogs_taken, seed=100 + i)
+    out_pinned.copy_(r.all_states[0], non_blocking=True)
+    cnt_pinned.copy_(r.trace[0], non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_grad += int(cnt_pinned.sum())
+    x_pinned.copy_(out_pinned)
+  e2e_s = time.perf_counter() - t0
+  ee = torch.tensor([float(e2e_grad), e2e_s], device=dev, dtype=torch.float64)
+  if world > 1:
+    g = [torch.zeros_like(ee) for _ in range(world)]
+    dist.all_gather(g, ee)
+    e2e_value = sum(float(v[0]) for v in g) / max(float(v[1]) for v in g)
+  else:
+    e2e_value = e2e_grad / e2e_s
+
+  # ---- min-ESS/s (second half of the metric): 200 traced draws per chain
+  ess_info = None
+  if not args.no_ess and rank == 0:
+    n_draws = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    draws = tfp.mcmc.sample_chain(n_draws, state, kernel=nuts, previous_kernel_results=pkr, trace_fn=None, seed=21)
+    e1.record()
+    torch.cuda.synchronize()
+    samp_s = e0.elapsed_time(e1) / 1e3
+    sub = draws[:, :2048].contiguous()
+    ess = tfp.mcmc.effective_sample_size(sub, filter_beyond_positive_pairs=True, filter_threshold=None)
+    per_dim = ess.sum(0) * (B / 2048.0)
+    cross = tfp.mcmc.effective_sample_size(sub, cross_chain_dims=1, filter_beyond_positive_pairs=True,
+                                           filter_threshold=None) * (B / 2048.0)
+    rhat = tfp.mcmc.potential_scale_reduction(sub, split_chains=True)
+    mean_err = float((draws.mean((0, 1)).abs() / torch.tensor(np.sqrt(np.diag(target.covariance)),
+                                                               device=dev, dtype=torch.float32)).max())
+    ess_info = {'min_ess_per_sec_sum_over_chains': float(per_dim.min()) / samp_s,
+                'min_ess_per_sec_cross_chain': float(cross.min()) / samp_s, 'draws_per_chain': n_draws,
+                'sampling_seconds': samp_s, 'max_split_rhat': float(rhat.max()),
+                'max_abs_mean_over_sd': mean_err,
+                'note': 'ESS on 2,048 of the chains scaled to all chains of rank 0'}
+    del draws, sub
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  pk, pk_src = peaks()
+  # roofline of the dominant kernel (chain_kernel<WarpG,4,DenseGaussianT,NUTS>): ALGORITHMIC flops =
+  # 2*D^2 per gradient evaluation; the contraction currently runs on the FP32 FMA pipe, reported against
+  # the dense TF32 tensor peak (= 1/2 of the measured sustained bf16 peak), see DESIGN.md section 5.
+  flops = 2.0 * D * D * (n_grad / max(len(step_ms), 1))
+  avg_launch_s = (sum(step_ms) / 1e3) / max(len(step_ms), 1)
+  achieved = flops / avg_launch_s / 1e12
+  peak = 0.5 * pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+  roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+              'traffic': None, 'peak_source': pk_src + ': 0.5 x bf16_tflops_sustained (dense TF32)',
+              'kernel': 'chain_kernel<WarpG,4,DenseGaussianT,NUTS> (FP32 FMA pipe in round 1)'}
+  cpu_baseline = None
+  if not args.no_cpu_baseline and world == 1:
+    cpu_baseline, _, _ = cpu_reference_arm(3, 1, budget_s=20.0)
+  line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+          'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps, 'higher_is_better': True,
+          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+          'clocks': clocks, 'gpu_launches': int(launches),
+          'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * D * 4,
+                  'd2h_bytes_per_step': B * D * 4 + B * 4, 'steps': e2e_steps,
+                  'api': 'tfp.mcmc.sample_chain(num_results=1) per step incl. bootstrap_results'},
+          'roofline': roofline, 'cpu_baseline': cpu_baseline, 'step_size': eps,
+          'leapfrogs_per_transition': n_grad / (B * args.steps),
+          'persistent_run': {'value': fused_value, 'unit': UNIT,
+                             'note': 'same K transitions in ONE pb2_run launch (no L2 flush possible inside)'},
+          'min_ess': ess_info}
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()
