@@ -195,6 +195,25 @@ int pb2_ess(pb2_ctx* ctx, const float* d_states, int N, int B, int D, float filt
 /* states [N,B,D] -> rhat [D] */
 int pb2_rhat(pb2_ctx* ctx, const float* d_states, int N, int B, int D, int split_chains, float* d_out);
 
+/* ---- lock-step path for ROW-SHARDED data (BASELINE config 5) ------------------------------
+ * The reference expresses this as a target whose log-likelihood is psum'd over a data axis
+ * (internal/distribute_lib.py:76-80,179-242; hmc_test.py:1223-1254) inside
+ * SimpleLeapfrogIntegrator; here every rank evaluates its rows for ALL chains at once, the
+ * caller all-reduces the packed result (NCCL over NVLink) and finishes with the prior. */
+/* X~ local rows [N, DP] (rows zero-padded to DP in {32,64,100} floats), labels y[N] (0/1),
+ * theta [B, D] -> d_packed [B, D+1] = (X~^T (y - sigmoid(X~ theta)) | sum_n log-lik). */
+int pb2_rowshard_logistic_grad(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
+                               const float* d_theta, int B, float* d_packed);
+/* grad = -theta + packed[:, :D]; logp = log N(theta; 0, I) + packed[:, D]
+ * (inference_gym logistic_regression.py:88-103, bayesian_model.py:100-102). */
+int pb2_rowshard_logistic_finish(pb2_ctx* ctx, const float* d_packed, const float* d_theta, int B, int D,
+                                 float* d_grad, float* d_logp);
+/* leapfrog pieces on [B,D] arrays (leapfrog_integrator.py:280-309,330-355):
+ * mode 0: v = m + (eps/2) g, x += eps v;  mode 1: v += eps g, x += eps v;
+ * mode 2: v += eps g, m_out = v - (eps/2) g. */
+int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_step, int step_kind,
+                          float* d_v, float* d_x, const float* d_g, const float* d_m_in, float* d_m_out);
+
 #ifdef __cplusplus
 }
 #endif

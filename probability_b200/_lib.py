@@ -102,8 +102,9 @@ def load():
         'pb2_da_apply': ([vp, vp, i32, ll, vp, vp], i32),
         'pb2_ess': ([vp, vp, i32, i32, i32, f32, i32, i32, i32, vp], i32),
         'pb2_rhat': ([vp, vp, i32, i32, i32, i32, vp], i32),
-        'pb2_rowshard_logistic_grad': ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp], i32),
-        'pb2_hmc_leapfrog_update': ([vp, i32, i32, vp, vp, vp, vp, f32, i32], i32),
+        'pb2_rowshard_logistic_grad': ([vp, vp, vp, i32, i32, i32, vp, i32, vp], i32),
+        'pb2_rowshard_logistic_finish': ([vp, vp, vp, i32, i32, vp, vp], i32),
+        'pb2_lockstep_leapfrog': ([vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp], i32),
     }
     for name, (argtypes, restype) in sig.items():
       try:

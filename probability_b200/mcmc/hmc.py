@@ -116,13 +116,17 @@ class UncalibratedHamiltonianMonteCarlo(kernel_base.TransitionKernel):
     seeds = pb_random.split_seed(seed, n=len(sizes))                      # hmc.py:685
     m0 = torch.cat([pb_random.normal((B, n), seed=seeds[i], device=x.device) for i, n in enumerate(sizes)],
                    dim=1).contiguous()                                    # hmc.py:689-695
-    ctx = _lib.Context.get(x.device)
-    ctx.bind_stream()
-    m1, x1, g1 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
-    lp1 = torch.empty_like(lp)
-    _lib.check(ctx.lib.pb2_leapfrog(ctx.handle, self._target.handle(ctx), B, _lib.ptr(m0), _lib.ptr(x),
-                                    _lib.ptr(lp), _lib.ptr(g), _lib.ptr(step), step_kind, L, _lib.ptr(m1),
-                                    _lib.ptr(x1), _lib.ptr(lp1), _lib.ptr(g1)), ctx.handle)
+    if getattr(self._target, 'is_lockstep', False):
+      # row-sharded data: all chains advance together, gradient all-reduced every leapfrog
+      m1, x1, lp1, g1 = self._target.leapfrog(m0, x, lp, g, step, step_kind, L)
+    else:
+      ctx = _lib.Context.get(x.device)
+      ctx.bind_stream()
+      m1, x1, g1 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+      lp1 = torch.empty_like(lp)
+      _lib.check(ctx.lib.pb2_leapfrog(ctx.handle, self._target.handle(ctx), B, _lib.ptr(m0), _lib.ptr(x),
+                                      _lib.ptr(lp), _lib.ptr(g), _lib.ptr(step), step_kind, L, _lib.ptr(m1),
+                                      _lib.ptr(x1), _lib.ptr(lp1), _lib.ptr(g1)), ctx.handle)
     s = (m0 * m0).sum(1) + (-(m1 * m1).sum(1))                            # hmc.py:862-875
     corr = 0.5 * torch.where(torch.isfinite(s), s, torch.full_like(s, -np.inf))
     res = pkr._replace(
@@ -223,8 +227,14 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
       return pkr.accepted_results.step_size, int(pkr.accepted_results.num_leapfrog_steps)
     return self.step_size, int(self.num_leapfrog_steps)
 
+  @property
+  def _lockstep(self):
+    return getattr(self._target, 'is_lockstep', False)
+
   def one_step(self, current_state, previous_kernel_results, seed=None):
     pkr = previous_kernel_results
+    if self._lockstep:   # MetropolisHastings(UncalibratedHMC) over the lock-step leapfrog
+      return self._impl.one_step(current_state, pkr, seed=seed)
     seed = pb_random.sanitize_seed(seed)
     x, shapes, was_list = _engine.flatten_state(current_state)
     x = x.clone()
@@ -268,7 +278,8 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
   def _fused_run(self, x, shapes, was_list, pkr, seed, num_results, num_burnin_steps,
                  num_steps_between_results, paths, da_state=None, step=None, leapfrog_total=None):
     """Runs all transitions in libpb2; returns (trace dict keyed by results path, final results, seed)."""
-    import torch
+    if self._lockstep:
+      return None     # row-sharded target: the step loop drives the per-leapfrog all-reduce
     acc = pkr.accepted_results
     B, D = x.shape
     g = _engine.flatten_state(list(acc.grads_target_log_prob))[0].clone()

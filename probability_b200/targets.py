@@ -153,6 +153,95 @@ class StochasticVolatility(Target):
     return out
 
 
+class RowShardedLogisticRegression(Target):
+  """Large-data logistic regression whose ROWS are sharded over the ranks of a
+  torch.distributed process group (BASELINE config 5).  Every rank holds all chains
+  (replicated, identical RNG: no fold_in_axis_index, like an unsharded state part in
+  hmc_test.py:1246-1272) and `features_local`/`labels_local`, its slice of the data.
+
+  One gradient evaluation = local pass over the rows for ALL chains (pb2_rowshard_logistic_grad)
+  + ONE all-reduce of the packed `[B, D+1]` (gradient | log-lik) buffer over NVLink (the psum of
+  distribute_lib.py:179-186 and its pbroadcast VJP :228-242) + prior (pb2_rowshard_logistic_finish).
+  Transitions with this target run lock-step over chains (one kernel sequence per leapfrog)."""
+  kind = None
+  is_lockstep = True
+
+  def __init__(self, features_local, labels_local, process_group=None, add_bias=True):
+    X = np.asarray(features_local, np.float32)
+    if add_bias:
+      X = np.concatenate([X, np.ones([X.shape[0], 1], np.float32)], axis=-1)
+    y = np.asarray(labels_local).astype(np.float32)
+    if y.shape != (X.shape[0],):
+      raise ValueError('labels_local must have shape [num_local_points]')
+    self.dim = X.shape[1]
+    self.n_rows = X.shape[0]
+    self.part_sizes = [self.dim]
+    if self.dim > 100:
+      raise ValueError('row-sharded logistic regression supports at most 100 weights (incl. bias)')
+    self.padded_dim = 32 if self.dim <= 32 else (64 if self.dim <= 64 else 100)
+    Xp = np.zeros([X.shape[0], self.padded_dim], np.float32)
+    Xp[:, :self.dim] = X
+    self._Xp = Xp
+    self._y = y
+    self.process_group = process_group
+    self._dev = {}
+
+  def _device_data(self, device):
+    import torch
+    key = device.index
+    if key not in self._dev:
+      self._dev[key] = (torch.from_numpy(self._Xp).to(device), torch.from_numpy(self._y).to(device))
+    return self._dev[key]
+
+  def handle(self, ctx):
+    raise _lib.Pb2Error('RowShardedLogisticRegression runs the lock-step path; it has no per-chain kernel')
+
+  def _world(self):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+      return dist
+    return None
+
+  def log_prob_and_grad(self, x):
+    import torch
+    if x.dim() != 2 or x.shape[1] != self.dim:
+      raise ValueError('expected state of shape [chains, {}], got {}'.format(self.dim, tuple(x.shape)))
+    x = x.contiguous().float()
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    X, y = self._device_data(x.device)
+    B = x.shape[0]
+    packed = torch.empty(B, self.dim + 1, dtype=torch.float32, device=x.device)
+    _lib.check(ctx.lib.pb2_rowshard_logistic_grad(ctx.handle, _lib.ptr(X), _lib.ptr(y), self.n_rows, self.dim,
+                                                  self.padded_dim, _lib.ptr(x), B, _lib.ptr(packed)), ctx.handle)
+    dist = self._world()
+    if dist is not None:
+      dist.all_reduce(packed, group=self.process_group)     # per-leapfrog gradient all-reduce (NCCL/NVLink)
+    lp = torch.empty(B, dtype=torch.float32, device=x.device)
+    g = torch.empty_like(x)
+    _lib.check(ctx.lib.pb2_rowshard_logistic_finish(ctx.handle, _lib.ptr(packed), _lib.ptr(x), B, self.dim,
+                                                    _lib.ptr(g), _lib.ptr(lp)), ctx.handle)
+    return lp, g
+
+  def leapfrog(self, m, x, lp, g, step, step_kind, num_steps):
+    """SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-309) lock-step over all chains."""
+    import torch
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    B, D = x.shape
+    x = x.clone()
+    v = torch.empty_like(x)
+    m_out = torch.empty_like(x)
+    call = lambda mode, gg: _lib.check(ctx.lib.pb2_lockstep_leapfrog(
+        ctx.handle, mode, B, D, _lib.ptr(step), step_kind, _lib.ptr(v), _lib.ptr(x), _lib.ptr(gg), _lib.ptr(m),
+        _lib.ptr(m_out)), ctx.handle)
+    call(0, g.contiguous())
+    for i in range(int(num_steps)):
+      lp, g = self.log_prob_and_grad(x)
+      call(1 if i + 1 < int(num_steps) else 2, g)
+    return m_out, x, lp, g
+
+
 def synthetic_sv_returns(T=2516, phi=0.95, s=0.25, m=None, seed=0):
   rng = np.random.default_rng(seed)
   m = 2.0 * np.log(15.0) if m is None else m
