@@ -1,6 +1,7 @@
 // extern "C" entry points of libpb2 (see include/pb2.h for the contract and the
 // reference interfaces each entry point replaces).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,6 +73,7 @@ int pb2_ctx_create(int device, pb2_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* v = getenv("PB2_DENSE_VARIANT")) c->dense_variant = atoi(v);
   if (int rc = check_cuda(c, cudaMalloc(&c->d_queue, 64), "cudaMalloc(queue)")) { delete c; return rc; }
   if (int rc = check_cuda(c, cudaMalloc(&c->d_partial, 64), "cudaMalloc(partial)")) { delete c; return rc; }
   *out = c;

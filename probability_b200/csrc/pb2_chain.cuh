@@ -217,6 +217,8 @@ struct Chain {
   // checkpoint store: [slot][j][lane]  (conflict-free in smem, coalesced in global)
   __device__ __forceinline__ static int ck_idx(int slot, int j, int lane) { return (slot * E + j) * Grp::G + lane; }
 
+  static constexpr int kChunk = Grp::G < 32 ? Grp::G : 32;
+
   struct NutsOut {
     float energy, log_accept_ratio;
     int leapfrogs;
@@ -286,9 +288,9 @@ struct Chain {
       const uint32_t* kud = ku + 2 * (nsteps - 1);
 #pragma unroll 1
       for (int i = 0; i < nsteps && c_prev; ++i) {
-        if ((i & 31) == 0) {  // next 32 multinomial uniforms of this chain, lane-parallel
+        if ((i & (kChunk - 1)) == 0) {  // next kChunk multinomial uniforms of this chain, lane-parallel
           grp.sync();
-          if (grp.lane < 32 && i + grp.lane < nsteps)
+          if (grp.lane < kChunk && i + grp.lane < nsteps)
             rb[32 + grp.lane] = log1pf(-uniform_from_bits(chain_bits(kud + 2 * (i + grp.lane)), 0.f, 1.f));
           grp.sync();
         }
@@ -347,7 +349,7 @@ struct Chain {
         const float dH = en - H0;
         const bool nd_i = (-dH) < p.max_energy_diff;  // :880
         const float w_new = log_add_exp(bw, dH);      // :881-883
-        const bool take = rb[32 + (i & 31)] <= (dH - w_new);  // :897-901
+        const bool take = rb[32 + (i & (kChunk - 1))] <= (dH - w_new);  // :897-901
         if (take) {
 #pragma unroll
           for (int j = 0; j < E; ++j) { bx[j] = sx[j]; bg[j] = sg[j]; }

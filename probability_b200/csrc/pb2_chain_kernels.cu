@@ -16,8 +16,8 @@ struct SmemPlan {
   int ck_floats;     // floats per checkpoint array (m or rho)
 };
 
-template <class Grp, int E, class Tgt, int MODE>
-__global__ void __launch_bounds__(512, 1)
+template <class Grp, int E, class Tgt, int MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io, const SmemPlan plan) {
   extern __shared__ __align__(16) float smem[];
   float* cta = smem;
@@ -26,7 +26,7 @@ chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io
   __syncthreads();
   float* gbase;
   if constexpr (Grp::kIsBlock) gbase = smem + plan.cta_floats + plan.red_floats;
-  else gbase = smem + plan.cta_floats + (threadIdx.x >> 5) * plan.group_floats;
+  else gbase = smem + plan.cta_floats + (threadIdx.x / Grp::G) * plan.group_floats;
   auto make_group = [&]() {
     if constexpr (Grp::kIsBlock) return Grp(gbase, smem + plan.cta_floats);
     else return Grp(gbase);
@@ -117,7 +117,7 @@ chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io
   }
 }
 
-template <class Grp, int E, class Tgt, int MODE>
+template <class Grp, int E, class Tgt, int MODE, int MAXT = 512>
 static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p, const PrimIO& io) {
   SmemPlan plan{};
   auto r4 = [](size_t v) { return (int)((v + 3) & ~size_t(3)); };
@@ -145,11 +145,12 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
   } else {
     if (cta_bytes + grp_bytes > (size_t)ctx->max_smem_optin)
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "target data does not fit in shared memory");
-    int wmax = (int)std::min<size_t>(16, (ctx->max_smem_optin - cta_bytes) / grp_bytes);
+    int wmax = (int)std::min<size_t>(MAXT / Grp::G, (ctx->max_smem_optin - cta_bytes) / grp_bytes);
     // small batches: spread chains over SMs (latency-bound); big batches: fill each SM
     int want = (p.B + ctx->num_sms - 1) / ctx->num_sms;
-    warps = std::max(1, std::min(wmax, want));
-    threads = warps * 32;
+    warps = std::max(1, std::min(wmax, want));          // groups per CTA
+    if (Grp::G < 32) warps = ((warps * Grp::G + 31) / 32) * (32 / Grp::G);   // whole warps
+    threads = warps * Grp::G;
     grid = std::min((p.B + warps - 1) / warps, ctx->num_sms);
   }
   const size_t smem_bytes = cta_bytes + (size_t)warps * grp_bytes;
@@ -163,7 +164,7 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
     }
     p.ckpt_global = ctx->d_ckpt;
   }
-  auto kfn = chain_kernel<Grp, E, Tgt, MODE>;
+  auto kfn = chain_kernel<Grp, E, Tgt, MODE, MAXT>;
   if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem_bytes), "cudaFuncSetAttribute"))
     return rc;
@@ -175,13 +176,13 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
   return check_cuda(ctx, cudaGetLastError(), "chain_kernel launch");
 }
 
-template <class Grp, int E, class Tgt>
+template <class Grp, int E, class Tgt, int MAXT = 512>
 static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
   switch (mode) {
-    case kModeLogpGrad: return launch_t<Grp, E, Tgt, kModeLogpGrad>(ctx, tp, p, io);
-    case kModeLeapfrog: return launch_t<Grp, E, Tgt, kModeLeapfrog>(ctx, tp, p, io);
-    case kModeHMC: return launch_t<Grp, E, Tgt, kModeHMC>(ctx, tp, p, io);
-    case kModeNUTS: return launch_t<Grp, E, Tgt, kModeNUTS>(ctx, tp, p, io);
+    case kModeLogpGrad: return launch_t<Grp, E, Tgt, kModeLogpGrad, MAXT>(ctx, tp, p, io);
+    case kModeLeapfrog: return launch_t<Grp, E, Tgt, kModeLeapfrog, MAXT>(ctx, tp, p, io);
+    case kModeHMC: return launch_t<Grp, E, Tgt, kModeHMC, MAXT>(ctx, tp, p, io);
+    case kModeNUTS: return launch_t<Grp, E, Tgt, kModeNUTS, MAXT>(ctx, tp, p, io);
   }
   return set_error(ctx, PB2_ERR_INVALID, "bad mode");
 }
@@ -196,7 +197,13 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
     case PB2_TARGET_DENSE_GAUSSIAN: {
       DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, D};
       if (D <= 32) return launch_mode<WarpG, 1, DenseGaussianT<WarpG, 1>>(ctx, tp, mode, p, io);
-      if (D <= 128) return launch_mode<WarpG, 4, DenseGaussianT<WarpG, 4>>(ctx, tp, mode, p, io);
+      if (D <= 128) {
+        // experiment kept for A/B profiling (PB2_DENSE_VARIANT=2): two chains per warp, 16 lanes x 8 elements,
+        // one LDS of a P row feeding both -- measured 0.6x of warp-per-chain on B200 (issue-bound, 8 warps/SM)
+        if (ctx->dense_variant == 2)
+          return launch_mode<HalfWarpG, 8, DenseGaussianT<HalfWarpG, 8>, 256>(ctx, tp, mode, p, io);
+        return launch_mode<WarpG, 4, DenseGaussianT<WarpG, 4>>(ctx, tp, mode, p, io);
+      }
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "dense Gaussian: D > 128 not supported");
     }
     case PB2_TARGET_LOGISTIC: {

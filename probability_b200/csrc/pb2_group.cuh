@@ -36,6 +36,35 @@ struct WarpG {
   __device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 };
 
+// Two chains per warp, 16 lanes each.  The halves run their own (divergent) control flow and only
+// re-converge -- __syncwarp(full mask) inside the target's contraction loop -- so that one
+// LDS of the shared operand (the precision matrix row) feeds both chains.
+struct HalfWarpG {
+  static constexpr int G = 16;
+  static constexpr bool kIsBlock = false;
+  int lane;        // 0..15 inside the half
+  unsigned mask;   // lanes of this half
+  float* scratch;
+  __device__ HalfWarpG(float* s)
+      : lane(threadIdx.x & 15), mask((threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu), scratch(s) {}
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ float sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 16);
+    return v;
+  }
+  template <int N>
+  __device__ __forceinline__ void sumN(float (&v)[N]) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(mask, v[i], o, 16);
+    }
+  }
+  __device__ __forceinline__ int bcast_int(int v, int src) { return __shfl_sync(mask, v, src, 16); }
+  __device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(mask, v, src, 16); }
+};
+
 template <int NW>
 struct BlockG {
   static constexpr int G = 32 * NW;

@@ -14,6 +14,7 @@ struct pb2_ctx {
   int num_sms = 148;
   int max_smem_optin = 227 * 1024;
   long long launches = 0;
+  int dense_variant = 0;           // 0: half-warp-per-chain (default), 1: warp-per-chain (A/B profiling)
   std::string err;
   int* d_queue = nullptr;          // dynamic chain queue counter
   float* d_ckpt = nullptr;         // global checkpoint scratch (block-group targets)

@@ -85,12 +85,12 @@ struct DenseGaussianParams {
 
 template <class Grp, int E>
 struct DenseGaussianT {
-  static_assert(!Grp::kIsBlock, "dense Gaussian runs warp-per-chain");
+  static_assert(!Grp::kIsBlock, "dense Gaussian runs (half-)warp-per-chain");
   using Params = DenseGaussianParams;
   static constexpr bool kCkptInSmem = true;
-  static constexpr int DP = 32 * E;  // padded row length
-  const float* sP;                   // CTA-shared [D][DP]
-  float* xbuf;                       // per-warp [DP]
+  static constexpr int DP = Grp::G * E;  // padded row length
+  const float* sP;                       // CTA-shared [D][DP]
+  float* xbuf;                           // per-group [DP]
   float loc[E];
   float lognorm;
   int D;
@@ -116,38 +116,51 @@ struct DenseGaussianT {
   __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
     float xc[E];
 #pragma unroll
-    for (int j = 0; j < E; ++j) {
-      xc[j] = x[j] - loc[j];
-      xbuf[grp.lane * E + j] = xc[j];
+    for (int j = 0; j < E; ++j) xc[j] = x[j] - loc[j];
+    if constexpr (E % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < E / 4; ++q)
+        *reinterpret_cast<float4*>(xbuf + grp.lane * E + 4 * q) =
+            make_float4(xc[4 * q], xc[4 * q + 1], xc[4 * q + 2], xc[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < E; ++j) xbuf[grp.lane * E + j] = xc[j];
     }
-    __syncwarp();
+    grp.sync();
+    // two chains per warp: re-converge the halves so ONE LDS of a P row feeds both chains
+    if constexpr (Grp::G == 16) __syncwarp();
     float acc[E];
 #pragma unroll
     for (int j = 0; j < E; ++j) acc[j] = 0.f;
     const float* prow = sP + grp.lane * E;
-    if constexpr (E == 4) {
-      // P symmetric: column block of row k == row block; LDS.128 per k, x_k broadcast (LDS.128 per 4 k)
+    if constexpr (E % 4 == 0) {
+      // P symmetric: the column block of row k equals the row block; x_k broadcast as LDS.128 per 4 k
       const int D4 = D & ~3;
       for (int k = 0; k < D4; k += 4) {
-        const float4 xk = *reinterpret_cast<const float4*>(xbuf + k);
-        const float4 p0 = *reinterpret_cast<const float4*>(prow + (k + 0) * DP);
-        const float4 p1 = *reinterpret_cast<const float4*>(prow + (k + 1) * DP);
-        const float4 p2 = *reinterpret_cast<const float4*>(prow + (k + 2) * DP);
-        const float4 p3 = *reinterpret_cast<const float4*>(prow + (k + 3) * DP);
-        acc[0] = fmaf(p0.x, xk.x, acc[0]); acc[1] = fmaf(p0.y, xk.x, acc[1]);
-        acc[2] = fmaf(p0.z, xk.x, acc[2]); acc[3] = fmaf(p0.w, xk.x, acc[3]);
-        acc[0] = fmaf(p1.x, xk.y, acc[0]); acc[1] = fmaf(p1.y, xk.y, acc[1]);
-        acc[2] = fmaf(p1.z, xk.y, acc[2]); acc[3] = fmaf(p1.w, xk.y, acc[3]);
-        acc[0] = fmaf(p2.x, xk.z, acc[0]); acc[1] = fmaf(p2.y, xk.z, acc[1]);
-        acc[2] = fmaf(p2.z, xk.z, acc[2]); acc[3] = fmaf(p2.w, xk.z, acc[3]);
-        acc[0] = fmaf(p3.x, xk.w, acc[0]); acc[1] = fmaf(p3.y, xk.w, acc[1]);
-        acc[2] = fmaf(p3.z, xk.w, acc[2]); acc[3] = fmaf(p3.w, xk.w, acc[3]);
+        const float4 xk4 = *reinterpret_cast<const float4*>(xbuf + k);
+        const float xs[4] = {xk4.x, xk4.y, xk4.z, xk4.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q) {
+            const float4 pv = *reinterpret_cast<const float4*>(prow + (k + kk) * DP + 4 * q);
+            acc[4 * q + 0] = fmaf(pv.x, xs[kk], acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(pv.y, xs[kk], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(pv.z, xs[kk], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(pv.w, xs[kk], acc[4 * q + 3]);
+          }
+        }
       }
       for (int k = D4; k < D; ++k) {
         const float xk = xbuf[k];
-        const float4 p0 = *reinterpret_cast<const float4*>(prow + k * DP);
-        acc[0] = fmaf(p0.x, xk, acc[0]); acc[1] = fmaf(p0.y, xk, acc[1]);
-        acc[2] = fmaf(p0.z, xk, acc[2]); acc[3] = fmaf(p0.w, xk, acc[3]);
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) {
+          const float4 pv = *reinterpret_cast<const float4*>(prow + k * DP + 4 * q);
+          acc[4 * q + 0] = fmaf(pv.x, xk, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(pv.y, xk, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(pv.z, xk, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(pv.w, xk, acc[4 * q + 3]);
+        }
       }
     } else {
       for (int k = 0; k < D; ++k) {
@@ -162,7 +175,7 @@ struct DenseGaussianT {
       g[j] = -acc[j];
       part = fmaf(xc[j], g[j], part);
     }
-    __syncwarp();  // xbuf is rewritten by the next call
+    grp.sync();  // xbuf is rewritten by the next call
     return fmaf(0.5f, grp.sum(part), lognorm);
   }
 };

@@ -45,7 +45,9 @@ def run(name, target, state, kernel, warm, steps, adapt=None):
 
 def main():
   dev = torch.device('cuda', 0)
-  which = sys.argv[1:] or ['c1', 'c2', 'c3', 'c4']
+  import os
+  which = [a for a in sys.argv[1:] if a.startswith('c')] or ['c1', 'c2', 'c3', 'c4']
+  noadapt = os.environ.get('PROBE_NOADAPT') == '1'   # profiling: skip adaptation, use known step sizes
   if 'c1' in which:
     tg = tfp.targets.EightSchools()
     st = [torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.ones(64, 8, device=dev)]
@@ -56,19 +58,21 @@ def main():
   if 'c2' in which:
     tg = tfp.targets.IllConditionedGaussian()
     st = torch.zeros(16384, 100, device=dev)
-    run('C2 dense-gaussian NUTS B=16384', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.158, max_tree_depth=10), 2, 10,
-        adapt=int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[1] == 'c2' else 60)
+    run('C2 dense-gaussian NUTS B=16384', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.74 if noadapt else 0.158, max_tree_depth=10), 2,
+        10, adapt=None if noadapt else 60)
   if 'c3' in which:
     X, y = tfp.targets.synthetic_logistic_data(1000, 24, seed=0)
     tg = tfp.targets.LogisticRegression(X, y)
     st = torch.zeros(8192, 25, device=dev)
-    run('C3 logistic NUTS B=8192', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.1, max_tree_depth=10), 2, 10, adapt=60)
+    run('C3 logistic NUTS B=8192', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.093 if noadapt else 0.1, max_tree_depth=10),
+        2, 10, adapt=None if noadapt else 60)
   if 'c4' in which:
     yv = tfp.targets.synthetic_sv_returns()
     tg = tfp.targets.StochasticVolatility(yv)
     st = torch.zeros(4096, 2519, device=dev)
     st[:, 1] = float(np.log(yv.var()))
-    run('C4 stoch-vol NUTS B=4096', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.02, max_tree_depth=10), 1, 3, adapt=30)
+    run('C4 stoch-vol NUTS B=4096', tg, st, tfp.mcmc.NoUTurnSampler(tg, 0.038 if noadapt else 0.02, max_tree_depth=10),
+        1, 3, adapt=None if noadapt else 30)
 
 
 if __name__ == '__main__':
