@@ -114,6 +114,12 @@ int pb2_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, c
                  const float* d_logp, const float* d_grad, const float* d_step, int step_kind,
                  int num_steps, float* d_m_out, float* d_x_out, float* d_logp_out, float* d_grad_out);
 
+/* Same contract as pb2_logp_grad for a dense-Gaussian target (D <= 100), evaluated for all chains at once
+ * on the tcgen05 tensor cores (128-chain tiles, 3xTF32 split, accumulator in TMEM).  pb2_logp_grad
+ * dispatches here for B >= 128. */
+int pb2_dense_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, float* d_logp,
+                           float* d_grad);
+
 /* ---- transitions / sample_chain -------------------------------------------------- */
 typedef struct {
   int kind;                 /* PB2_KERNEL_HMC | PB2_KERNEL_NUTS */
