@@ -84,6 +84,7 @@ def load():
         'pb2_ctx_synchronize': ([vp], i32),
         'pb2_last_error': ([vp], C.c_char_p),
         'pb2_launch_count': ([vp], ll),
+        'pb2_ctx_set_int': ([vp, C.c_char_p, i32], i32),
         'pb2_target_create': ([vp, C.POINTER(TargetDesc), C.POINTER(vp)], i32),
         'pb2_target_destroy': ([vp], i32),
         'pb2_target_dim': ([vp], i32),
@@ -179,6 +180,9 @@ class Context:
 
   def launch_count(self):
     return int(self.lib.pb2_launch_count(self.handle))
+
+  def set_int(self, name, value):
+    check(self.lib.pb2_ctx_set_int(self.handle, name.encode(), int(value)), self.handle)
 
   def synchronize(self):
     check(self.lib.pb2_ctx_synchronize(self.handle), self.handle)

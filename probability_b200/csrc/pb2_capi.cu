@@ -106,6 +106,15 @@ int pb2_ctx_synchronize(pb2_ctx* ctx) {
 
 long long pb2_launch_count(pb2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return PB2_ERR_INVALID;
+  if (std::strcmp(name, "dense_variant") == 0) {
+    ctx->dense_variant = value;
+    return PB2_OK;
+  }
+  return set_error(ctx, PB2_ERR_INVALID, std::string("pb2_ctx_set_int: unknown option ") + name);
+}
+
 // ------------------------------------------------------------------ targets
 int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* d, pb2_target** out) {
   if (!ctx || !d || !out) return set_error(ctx, PB2_ERR_INVALID, "pb2_target_create: NULL argument");

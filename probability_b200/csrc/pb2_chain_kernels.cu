@@ -189,6 +189,7 @@ static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, C
 
 int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io) {
   const int D = tgt->dim;
+  if (tile_path_supported(ctx, tgt, mode, p)) return launch_tile_chain(ctx, tgt, mode, p);
   switch (tgt->kind) {
     case PB2_TARGET_EIGHT_SCHOOLS: {
       EightSchoolsParams tp{tgt->d_a, tgt->d_b, tgt->n_rows};

@@ -61,6 +61,10 @@ int check_cuda(pb2_ctx* ctx, cudaError_t e, const char* what);
 // pb2_chain_kernels.cu
 int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io);
 
+// pb2_tile.cu (tcgen05 128-chain tiles, dense Gaussian)
+bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p);
+int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
+
 // pb2_misc.cu
 int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);
 int launch_nuts_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int max_depth, int layout,
