@@ -150,11 +150,269 @@ tile_hmc_kernel(const ChainParams p, const DenseGaussianParams tp) {
   cx.finish();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tile_nuts_kernel: NoUTurnSampler.one_step (tfp/mcmc/nuts.py:321-946) for a tile of 128 chains run
+// in LOCK-STEP, i.e. literally the reference's batched algorithm (shared doubling / leaf counters,
+// per-chain masks), which makes every leapfrog of the tile one tensor-core contraction.
+//   registers : moving trajectory end (x, m, g) of my 26-dim slice, per-chain scalars (replicated x4)
+//   TMEM      : rho_subtree (cumulative momentum of the subtree) next to the MMA operands
+//   L2 scratch: other end, trajectory / subtree candidates, rho, the popcount-indexed checkpoint
+//               stores -- laid out [vector][dim][chain] so a warp's access is one 128 B line
+enum { kVOx = 0, kVOm, kVOg, kVCx, kVCg, kVBx, kVBg, kVRho, kVCk };   // checkpoints: kVCk + slot (m), + depth + slot (rho)
+
+#define PB2_SCR(vec, j) scr[((size_t)(vec) * kKP + (size_t)(kK * cx.slice + (j))) * kM + cx.cl]
+
+__global__ void __launch_bounds__(kThreads, 1)
+tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __restrict__ scratch_all) {
+  extern __shared__ __align__(128) unsigned char planes[];
+  __shared__ Shared sh;
+  __shared__ float lu[4][kM];   // log1p(-u) of the multinomial draws of 4 consecutive leaves
+  Ctx cx;
+  cx.init(&sh, planes, tp.P, tp.loc, tp.D);
+  const int D = tp.D;
+  const int nvec = kVCk + 2 * p.max_depth;
+  float* scr = scratch_all + (size_t)blockIdx.x * nvec * kKP * kM;
+  const uint32_t rho_addr = cx.lane_addr + kColRho + kK * cx.slice;
+  const int ntiles = (p.B + kM - 1) / kM;
+  for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    const int c = tile_i * kM + cx.cl;
+    const bool live = c < p.B;
+    const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)c;
+    float x[kK], m[kK], g[kK];
+    tile_load(p.x, c, D, cx.slice, live, x);
+    tile_load(p.g, c, D, cx.slice, live, g);
+    float lp = live ? p.lp[c] : 0.f;
+    unsigned long long nleap_total = 0;
+#pragma unroll 1
+    for (int t = p.t0; t < p.t1; ++t) {
+      const float eps_abs = p.step_kind == 0 ? p.step[0] : (live ? p.step[c] : 0.f);
+      const uint32_t* sk = p.sched + (size_t)(t - p.t_sched0) * p.sched_stride;
+      const uint32_t* hdr = sk + 2 * p.n_parts;
+      const uint32_t* ku = hdr + 6 * p.max_depth;
+      const int r = tile_result_index(p, t);
+      // ---- _start_trajectory_batched (nuts.py:512-539): momentum, H0; both ends, candidate, rho
+      float s1[1] = {0.f};
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const int d = kK * cx.slice + j;
+        const float mm = (live && d < D) ? tile_momentum(p, sk, cg, d) : 0.f;
+        m[j] = mm;
+        s1[0] = fmaf(mm, mm, s1[0]);
+        PB2_SCR(kVOx, j) = x[j]; PB2_SCR(kVOm, j) = mm; PB2_SCR(kVOg, j) = g[j];
+        PB2_SCR(kVCx, j) = x[j]; PB2_SCR(kVCg, j) = g[j];
+        PB2_SCR(kVRho, j) = mm;
+      }
+      cx.reduce<1>(s1);
+      const float H0 = lp - 0.5f * s1[0];
+      float slp = lp, olp = lp, clp = lp, cen = H0, cw = 0.f;
+      float esum = 0.f;
+      int nleap = 0;
+      bool cont = live, notdiv = true, accepted = false, s_is_right = true;
+      int any_cont = __syncthreads_or(cont ? 1 : 0);
+#pragma unroll 1
+      for (int it = 0; it < p.max_depth && any_cont; ++it) {
+        // per-depth randoms of this chain (nuts.py:551-558, :622-625)
+        Key kd{hdr[6 * it], hdr[6 * it + 1]}, kac{hdr[6 * it + 2], hdr[6 * it + 3]};
+        const bool dir = (bits_at(kd, cg, (uint64_t)p.B_global, p.layout) & 1u) != 0;
+        const float lacc = log1pf(-uniform_from_bits(bits_at(kac, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
+        if (dir != s_is_right) {   // registers must hold the end that is extended
+#pragma unroll
+          for (int j = 0; j < kK; ++j) {
+            float a;
+            a = PB2_SCR(kVOx, j); PB2_SCR(kVOx, j) = x[j]; x[j] = a;
+            a = PB2_SCR(kVOm, j); PB2_SCR(kVOm, j) = m[j]; m[j] = a;
+            a = PB2_SCR(kVOg, j); PB2_SCR(kVOg, j) = g[j]; g[j] = a;
+          }
+          const float a = slp; slp = olp; olp = a;
+          s_is_right = dir;
+        }
+        const float eps = dir ? eps_abs : -eps_abs;
+        const float heps = 0.5f * eps;
+        // _build_sub_tree init (nuts.py:713-791)
+        {
+          uint32_t z[kK];
+#pragma unroll
+          for (int j = 0; j < kK; ++j) {
+            PB2_SCR(kVBx, j) = x[j]; PB2_SCR(kVBg, j) = g[j];
+            z[j] = 0u;
+          }
+          tmem_st26(rho_addr, z);
+        }
+        float blp = slp, ben = slp, bw = -INFINITY;
+        int n = 0;
+        bool c_prev = cont, nd = notdiv;
+        float esum_sub = 0.f;
+        const int nsteps = 1 << it;
+        const uint32_t* kud = ku + 2 * (nsteps - 1);
+        int any_prev = any_cont;
+#pragma unroll 1
+        for (int i = 0; i < nsteps && any_prev; ++i) {
+          if ((i & 3) == 0 && i + cx.slice < nsteps) {   // 4 leaves of multinomial uniforms, one per slice
+            Key kk{kud[2 * (i + cx.slice)], kud[2 * (i + cx.slice) + 1]};
+            lu[cx.slice][cx.cl] =
+                log1pf(-uniform_from_bits(bits_at(kk, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
+          }
+          // one leapfrog (leapfrog_integrator.py:280-309 with L = unrolled_leapfrog_steps)
+#pragma unroll
+          for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
+#pragma unroll 1
+          for (int l = 0; l < p.unrolled; ++l) {
+#pragma unroll
+            for (int j = 0; j < kK; ++j) x[j] = x[j] + eps * m[j];
+            cx.stage_a(x);
+            cx.contract();
+            cx.load_d(g);
+#pragma unroll
+            for (int j = 0; j < kK; ++j) m[j] = m[j] + eps * g[j];
+          }
+#pragma unroll
+          for (int j = 0; j < kK; ++j) m[j] = m[j] - heps * g[j];
+          n += c_prev ? 1 : 0;
+          // rho_subtree, checkpoint store / U-turn checks (nuts.py:826-869, 949-1010)
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};   // <x - mu, g>, |m|^2, U-turn dots of the first check
+          bool ok = true;
+          const int pc = __popc(i);
+          {
+            uint32_t rt[kK];
+            tmem_ld26(rho_addr, rt);
+            if ((i & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < kK; ++j) {
+                PB2_SCR(kVCk + pc, j) = m[j];
+                PB2_SCR(kVCk + p.max_depth + pc, j) = __uint_as_float(rt[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < kK; ++j) {
+              const float rn = __uint_as_float(rt[j]) + m[j];
+              rt[j] = __float_as_uint(rn);
+              s4[0] = fmaf(x[j] - sh.loc[kK * cx.slice + j], g[j], s4[0]);
+              s4[1] = fmaf(m[j], m[j], s4[1]);
+            }
+            tmem_st26(rho_addr, rt);
+            if (i & 1) {
+              const int k0 = pc - (__ffs(~i) - 1);
+#pragma unroll
+              for (int j = 0; j < kK; ++j) {
+                const float diff = __uint_as_float(rt[j]) - PB2_SCR(kVCk + p.max_depth + k0, j);
+                s4[2] = fmaf(diff, PB2_SCR(kVCk + k0, j), s4[2]);
+                s4[3] = fmaf(diff, m[j], s4[3]);
+              }
+            }
+          }
+          cx.reduce<4>(s4);
+          slp = fmaf(0.5f, s4[0], tp.lognorm);
+          if (i & 1) {
+            ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
+            const int k0 = pc - (__ffs(~i) - 1);
+#pragma unroll 1
+            for (int k = k0 + 1; k < pc; ++k) {   // uniform trip count over the tile (lock-step leaf index)
+              uint32_t rt[kK];
+              tmem_ld26(rho_addr, rt);
+              float s2[2] = {0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < kK; ++j) {
+                const float diff = __uint_as_float(rt[j]) - PB2_SCR(kVCk + p.max_depth + k, j);
+                s2[0] = fmaf(diff, PB2_SCR(kVCk + k, j), s2[0]);
+                s2[1] = fmaf(diff, m[j], s2[1]);
+              }
+              cx.reduce<2>(s2);
+              ok = ok && (s2[0] >= 0.f) && (s2[1] >= 0.f);
+            }
+          }
+          float en = slp - 0.5f * s4[1];                 // nuts.py:871-877
+          en = isnan(en) ? -INFINITY : en;
+          const float dH = en - H0;
+          const bool nd_i = (-dH) < p.max_energy_diff;   // :880
+          const float w_new = log_add_exp(bw, dH);       // :881-883
+          const bool take = lu[i & 3][cx.cl] <= (dH - w_new);   // :897-901
+          if (take) {
+#pragma unroll
+            for (int j = 0; j < kK; ++j) { PB2_SCR(kVBx, j) = x[j]; PB2_SCR(kVBg, j) = g[j]; }
+            blp = slp; ben = en;
+          }
+          bw = w_new;
+          const bool c_now = nd_i && c_prev;             // :921
+          if (c_now) esum_sub += expf(fminf(dH, 0.f));   // :930-933
+          nd = nd && (c_prev ? nd_i : true);             // :924-927,944
+          c_prev = ok && c_now;                          // :922
+          any_prev = __syncthreads_or(c_prev ? 1 : 0);   // nuts.py:759 reduce_any(continue_tree)
+        }
+        const bool cont_f = c_prev;
+        // _loop_tree_doubling tail (nuts.py:597-711)
+        esum = esum_sub + esum;
+        const float tw = cont_f ? bw : -INFINITY;
+        const float wsum = log_add_exp(tw, cw);
+        float thr = tw - cw;
+        thr = isnan(thr) ? 0.f : thr;
+        const bool swap = (lacc <= thr) && cont_f;
+        cw = wsum;
+        if (swap) {
+#pragma unroll
+          for (int j = 0; j < kK; ++j) { PB2_SCR(kVCx, j) = PB2_SCR(kVBx, j); PB2_SCR(kVCg, j) = PB2_SCR(kVBg, j); }
+          clp = blp; cen = ben;
+        }
+        float s2[2] = {0.f, 0.f};
+        {
+          uint32_t rt[kK];
+          tmem_ld26(rho_addr, rt);
+#pragma unroll
+          for (int j = 0; j < kK; ++j) {
+            const float rr = PB2_SCR(kVRho, j) + __uint_as_float(rt[j]);
+            PB2_SCR(kVRho, j) = rr;
+            s2[0] = fmaf(rr, m[j], s2[0]);
+            s2[1] = fmaf(rr, PB2_SCR(kVOm, j), s2[1]);
+          }
+        }
+        cx.reduce<2>(s2);
+        nleap += n;
+        accepted = accepted || swap;
+        notdiv = nd;
+        cont = cont_f && (s2[0] >= 0.f) && (s2[1] >= 0.f);
+        any_cont = __syncthreads_or(cont ? 1 : 0);       // nuts.py:404-407
+      }
+      // ---- results (nuts.py:424-445); the next state is the trajectory candidate
+#pragma unroll
+      for (int j = 0; j < kK; ++j) { x[j] = PB2_SCR(kVCx, j); g[j] = PB2_SCR(kVCg, j); }
+      lp = clp;
+      const int leap = nleap * p.unrolled;
+      nleap_total += (unsigned long long)leap;
+      const float lar = logf(esum / (float)nleap);
+      if (live && cx.slice == 0 && p.lar_last) p.lar_last[c] = lar;
+      if (r >= 0) {
+        const Trace& tr = p.tr;
+        if (tr.states) tile_store(tr.states, r, p.B, c, D, cx.slice, live, x);
+        if (tr.grads) tile_store(tr.grads, r, p.B, c, D, cx.slice, live, g);
+        if (live && cx.slice == 0) {
+          const size_t o = (size_t)r * p.B + c;
+          if (tr.target_log_prob) tr.target_log_prob[o] = lp;
+          if (tr.log_accept_ratio) tr.log_accept_ratio[o] = lar;
+          if (tr.is_accepted) tr.is_accepted[o] = accepted ? 1 : 0;
+          if (tr.leapfrogs_taken) tr.leapfrogs_taken[o] = leap;
+          if (tr.has_divergence) tr.has_divergence[o] = notdiv ? 0 : 1;
+          if (tr.reach_max_depth) tr.reach_max_depth[o] = cont ? 1 : 0;
+          if (tr.energy) tr.energy[o] = cen;
+          if (tr.step_size && c == 0 && p.step_kind == 0) tr.step_size[r] = p.step[0];
+        }
+      }
+    }
+    tile_store(p.x, 0, p.B, c, D, cx.slice, live, x);
+    tile_store(p.g, 0, p.B, c, D, cx.slice, live, g);
+    if (live && cx.slice == 0) {
+      p.lp[c] = lp;
+      if (p.leapfrog_total) p.leapfrog_total[c] += nleap_total;
+    }
+  }
+  cx.finish();
+}
+#undef PB2_SCR
+
 bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p) {
   if (ctx->dense_variant == 1) return false;                       // PB2_DENSE_VARIANT=1: force warp-per-chain
   if (tgt->kind != PB2_TARGET_DENSE_GAUSSIAN) return false;
   if (tgt->dim <= 32 || tgt->dim > 100) return false;
-  if (mode != kModeHMC) return false;
+  if (mode != kModeHMC && mode != kModeNUTS) return false;
   if (p.step_kind == 1) return false;                              // per-dimension step sizes: warp kernels
   return p.B >= 2 * kM;
 }
@@ -171,6 +429,23 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     tile_hmc_kernel<<<grid, kThreads, smem, ctx->stream>>>(p, tp);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "tile_hmc_kernel");
+  }
+  if (mode == kModeNUTS) {
+    const size_t per_cta = (size_t)(kVCk + 2 * p.max_depth) * kKP * kM * sizeof(float);
+    const size_t need = per_cta * grid;
+    if (need > ctx->ckpt_bytes) {
+      if (ctx->d_ckpt) cudaFree(ctx->d_ckpt);
+      ctx->d_ckpt = nullptr;
+      ctx->ckpt_bytes = 0;
+      if (int rc = check_cuda(ctx, cudaMalloc(&ctx->d_ckpt, need), "cudaMalloc(tile scratch)")) return rc;
+      ctx->ckpt_bytes = need;
+    }
+    if (int rc = check_cuda(ctx, cudaFuncSetAttribute(tile_nuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)smem), "cudaFuncSetAttribute(tile_nuts)"))
+      return rc;
+    tile_nuts_kernel<<<grid, kThreads, smem, ctx->stream>>>(p, tp, ctx->d_ckpt);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "tile_nuts_kernel");
   }
   return set_error(ctx, PB2_ERR_UNSUPPORTED, "tile path: unsupported mode");
 }
