@@ -161,8 +161,6 @@ tile_hmc_kernel(const ChainParams p, const DenseGaussianParams tp) {
 //               stores -- laid out [vector][dim][chain] so a warp's access is one 128 B line
 enum { kVOx = 0, kVOm, kVOg, kVCx, kVCg, kVBx, kVBg, kVRho, kVCk };   // checkpoints: kVCk + slot (m), + depth + slot (rho)
 
-#define PB2_SCR(vec, j) scr[((size_t)(vec) * kKP + (size_t)(kK * cx.slice + (j))) * kM + cx.cl]
-
 __global__ void __launch_bounds__(kThreads, 1)
 tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __restrict__ scratch_all) {
   extern __shared__ __align__(128) unsigned char planes[];
@@ -172,9 +170,14 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   cx.init(&sh, planes, tp.P, tp.loc, tp.D);
   const int D = tp.D;
   const int nvec = kVCk + 2 * p.max_depth;
-  float* scr = scratch_all + (size_t)blockIdx.x * nvec * kKP * kM;
+  constexpr size_t kVS = (size_t)kKP * kM;   // floats per scratch vector
+  // element j of scratch vector v of my (slice, chain): sv(v)[j * kM]
+  float* const scr_t = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM + cx.cl;
+  auto sv = [&](int v) -> float* { return scr_t + (size_t)v * kVS; };
+  const float* lc = sh.loc + kK * cx.slice;
   const uint32_t rho_addr = cx.lane_addr + kColRho + kK * cx.slice;
   const int ntiles = (p.B + kM - 1) / kM;
+  unsigned gt = 0;   // global leaf counter (rotates the "somebody continues" flags)
   for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
     const int c = tile_i * kM + cx.cl;
     const bool live = c < p.B;
@@ -193,15 +196,18 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
       const int r = tile_result_index(p, t);
       // ---- _start_trajectory_batched (nuts.py:512-539): momentum, H0; both ends, candidate, rho
       float s1[1] = {0.f};
+      {
+        float *ox = sv(kVOx), *om = sv(kVOm), *og = sv(kVOg), *ccx = sv(kVCx), *ccg = sv(kVCg), *rh = sv(kVRho);
 #pragma unroll
-      for (int j = 0; j < kK; ++j) {
-        const int d = kK * cx.slice + j;
-        const float mm = (live && d < D) ? tile_momentum(p, sk, cg, d) : 0.f;
-        m[j] = mm;
-        s1[0] = fmaf(mm, mm, s1[0]);
-        PB2_SCR(kVOx, j) = x[j]; PB2_SCR(kVOm, j) = mm; PB2_SCR(kVOg, j) = g[j];
-        PB2_SCR(kVCx, j) = x[j]; PB2_SCR(kVCg, j) = g[j];
-        PB2_SCR(kVRho, j) = mm;
+        for (int j = 0; j < kK; ++j) {
+          const int d = kK * cx.slice + j;
+          const float mm = (live && d < D) ? tile_momentum(p, sk, cg, d) : 0.f;
+          m[j] = mm;
+          s1[0] = fmaf(mm, mm, s1[0]);
+          ox[j * kM] = x[j]; om[j * kM] = mm; og[j * kM] = g[j];
+          ccx[j * kM] = x[j]; ccg[j * kM] = g[j];
+          rh[j * kM] = mm;
+        }
       }
       cx.reduce<1>(s1);
       const float H0 = lp - 0.5f * s1[0];
@@ -217,12 +223,13 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         const bool dir = (bits_at(kd, cg, (uint64_t)p.B_global, p.layout) & 1u) != 0;
         const float lacc = log1pf(-uniform_from_bits(bits_at(kac, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
         if (dir != s_is_right) {   // registers must hold the end that is extended
+          float *ox = sv(kVOx), *om = sv(kVOm), *og = sv(kVOg);
 #pragma unroll
           for (int j = 0; j < kK; ++j) {
             float a;
-            a = PB2_SCR(kVOx, j); PB2_SCR(kVOx, j) = x[j]; x[j] = a;
-            a = PB2_SCR(kVOm, j); PB2_SCR(kVOm, j) = m[j]; m[j] = a;
-            a = PB2_SCR(kVOg, j); PB2_SCR(kVOg, j) = g[j]; g[j] = a;
+            a = ox[j * kM]; ox[j * kM] = x[j]; x[j] = a;
+            a = om[j * kM]; om[j * kM] = m[j]; m[j] = a;
+            a = og[j * kM]; og[j * kM] = g[j]; g[j] = a;
           }
           const float a = slp; slp = olp; olp = a;
           s_is_right = dir;
@@ -231,13 +238,16 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         const float heps = 0.5f * eps;
         // _build_sub_tree init (nuts.py:713-791)
         {
-          uint32_t z[kK];
+          float *bx = sv(kVBx), *bg = sv(kVBg);
 #pragma unroll
-          for (int j = 0; j < kK; ++j) {
-            PB2_SCR(kVBx, j) = x[j]; PB2_SCR(kVBg, j) = g[j];
-            z[j] = 0u;
-          }
-          tmem_st26(rho_addr, z);
+          for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
+          for_chunks([&](auto off, auto n) {
+            constexpr int OFF = decltype(off)::value, N = decltype(n)::value;
+            uint32_t z[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) z[j] = 0u;
+            tmem_st<N>(rho_addr + OFF, z);
+          });
         }
         float blp = slp, ben = slp, bw = -INFINITY;
         int n = 0;
@@ -245,9 +255,8 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         float esum_sub = 0.f;
         const int nsteps = 1 << it;
         const uint32_t* kud = ku + 2 * (nsteps - 1);
-        int any_prev = any_cont;
 #pragma unroll 1
-        for (int i = 0; i < nsteps && any_prev; ++i) {
+        for (int i = 0; i < nsteps; ++i, ++gt) {
           if ((i & 3) == 0 && i + cx.slice < nsteps) {   // 4 leaves of multinomial uniforms, one per slice
             Key kk{kud[2 * (i + cx.slice)], kud[2 * (i + cx.slice) + 1]};
             lu[cx.slice][cx.cl] =
@@ -256,67 +265,88 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
           // one leapfrog (leapfrog_integrator.py:280-309 with L = unrolled_leapfrog_steps)
 #pragma unroll
           for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
+          bool stop = false;
 #pragma unroll 1
           for (int l = 0; l < p.unrolled; ++l) {
 #pragma unroll
             for (int j = 0; j < kK; ++j) x[j] = x[j] + eps * m[j];
             cx.stage_a(x);
             cx.contract();
+            if (l == 0) {
+              // nuts.py:759 reduce_any(continue_tree): flag raised at the end of the previous leaf; leaving
+              // mid-leaf is harmless because no chain of the tile continues (ends/candidates are final)
+              if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
+              if (threadIdx.x == 0) sh.flags[(gt + 1) & 3] = 0;
+            }
+            if (stop) break;
             cx.load_d(g);
 #pragma unroll
             for (int j = 0; j < kK; ++j) m[j] = m[j] + eps * g[j];
           }
+          if (stop) break;
 #pragma unroll
           for (int j = 0; j < kK; ++j) m[j] = m[j] - heps * g[j];
           n += c_prev ? 1 : 0;
-          // rho_subtree, checkpoint store / U-turn checks (nuts.py:826-869, 949-1010)
+          // rho_subtree, checkpoint store / U-turn checks (nuts.py:826-869, 949-1010), chunk by chunk
           float s4[4] = {0.f, 0.f, 0.f, 0.f};   // <x - mu, g>, |m|^2, U-turn dots of the first check
-          bool ok = true;
           const int pc = __popc(i);
-          {
-            uint32_t rt[kK];
-            tmem_ld26(rho_addr, rt);
-            if ((i & 1) == 0) {
+          const bool odd = (i & 1) != 0;
+          const int k0 = pc - (__ffs(~i) - 1);
+          float* ckm_w = sv(kVCk + pc);
+          float* ckr_w = sv(kVCk + p.max_depth + pc);
+          const float* ckm_r = sv(kVCk + k0);
+          const float* ckr_r = sv(kVCk + p.max_depth + k0);
+          for_chunks([&](auto off, auto nn) {
+            constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+            uint32_t rt[N];
+            tmem_ld<N>(rho_addr + OFF, rt);
+            tmem_wait_ld();
+            if (!odd) {
 #pragma unroll
-              for (int j = 0; j < kK; ++j) {
-                PB2_SCR(kVCk + pc, j) = m[j];
-                PB2_SCR(kVCk + p.max_depth + pc, j) = __uint_as_float(rt[j]);
+              for (int j = 0; j < N; ++j) {
+                ckm_w[(OFF + j) * kM] = m[OFF + j];
+                ckr_w[(OFF + j) * kM] = __uint_as_float(rt[j]);
               }
             }
 #pragma unroll
-            for (int j = 0; j < kK; ++j) {
-              const float rn = __uint_as_float(rt[j]) + m[j];
+            for (int j = 0; j < N; ++j) {
+              const float rn = __uint_as_float(rt[j]) + m[OFF + j];
               rt[j] = __float_as_uint(rn);
-              s4[0] = fmaf(x[j] - sh.loc[kK * cx.slice + j], g[j], s4[0]);
-              s4[1] = fmaf(m[j], m[j], s4[1]);
+              s4[0] = fmaf(x[OFF + j] - lc[OFF + j], g[OFF + j], s4[0]);
+              s4[1] = fmaf(m[OFF + j], m[OFF + j], s4[1]);
             }
-            tmem_st26(rho_addr, rt);
-            if (i & 1) {
-              const int k0 = pc - (__ffs(~i) - 1);
+            tmem_st<N>(rho_addr + OFF, rt);
+            if (odd) {
 #pragma unroll
-              for (int j = 0; j < kK; ++j) {
-                const float diff = __uint_as_float(rt[j]) - PB2_SCR(kVCk + p.max_depth + k0, j);
-                s4[2] = fmaf(diff, PB2_SCR(kVCk + k0, j), s4[2]);
-                s4[3] = fmaf(diff, m[j], s4[3]);
+              for (int j = 0; j < N; ++j) {
+                const float diff = __uint_as_float(rt[j]) - ckr_r[(OFF + j) * kM];
+                s4[2] = fmaf(diff, ckm_r[(OFF + j) * kM], s4[2]);
+                s4[3] = fmaf(diff, m[OFF + j], s4[3]);
               }
             }
-          }
+          });
           cx.reduce<4>(s4);
           slp = fmaf(0.5f, s4[0], tp.lognorm);
-          if (i & 1) {
+          bool ok = true;
+          if (odd) {
             ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
-            const int k0 = pc - (__ffs(~i) - 1);
 #pragma unroll 1
             for (int k = k0 + 1; k < pc; ++k) {   // uniform trip count over the tile (lock-step leaf index)
-              uint32_t rt[kK];
-              tmem_ld26(rho_addr, rt);
+              const float* km = sv(kVCk + k);
+              const float* kr = sv(kVCk + p.max_depth + k);
               float s2[2] = {0.f, 0.f};
+              for_chunks([&](auto off, auto nn) {
+                constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+                uint32_t rt[N];
+                tmem_ld<N>(rho_addr + OFF, rt);
+                tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < kK; ++j) {
-                const float diff = __uint_as_float(rt[j]) - PB2_SCR(kVCk + p.max_depth + k, j);
-                s2[0] = fmaf(diff, PB2_SCR(kVCk + k, j), s2[0]);
-                s2[1] = fmaf(diff, m[j], s2[1]);
-              }
+                for (int j = 0; j < N; ++j) {
+                  const float diff = __uint_as_float(rt[j]) - kr[(OFF + j) * kM];
+                  s2[0] = fmaf(diff, km[(OFF + j) * kM], s2[0]);
+                  s2[1] = fmaf(diff, m[OFF + j], s2[1]);
+                }
+              });
               cx.reduce<2>(s2);
               ok = ok && (s2[0] >= 0.f) && (s2[1] >= 0.f);
             }
@@ -328,8 +358,9 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
           const float w_new = log_add_exp(bw, dH);       // :881-883
           const bool take = lu[i & 3][cx.cl] <= (dH - w_new);   // :897-901
           if (take) {
+            float *bx = sv(kVBx), *bg = sv(kVBg);
 #pragma unroll
-            for (int j = 0; j < kK; ++j) { PB2_SCR(kVBx, j) = x[j]; PB2_SCR(kVBg, j) = g[j]; }
+            for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
             blp = slp; ben = en;
           }
           bw = w_new;
@@ -337,7 +368,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
           if (c_now) esum_sub += expf(fminf(dH, 0.f));   // :930-933
           nd = nd && (c_prev ? nd_i : true);             // :924-927,944
           c_prev = ok && c_now;                          // :922
-          any_prev = __syncthreads_or(c_prev ? 1 : 0);   // nuts.py:759 reduce_any(continue_tree)
+          if (c_prev) sh.flags[gt & 3] = 1;
         }
         const bool cont_f = c_prev;
         // _loop_tree_doubling tail (nuts.py:597-711)
@@ -349,21 +380,28 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         const bool swap = (lacc <= thr) && cont_f;
         cw = wsum;
         if (swap) {
+          float *bx = sv(kVBx), *bg = sv(kVBg), *ccx = sv(kVCx), *ccg = sv(kVCg);
 #pragma unroll
-          for (int j = 0; j < kK; ++j) { PB2_SCR(kVCx, j) = PB2_SCR(kVBx, j); PB2_SCR(kVCg, j) = PB2_SCR(kVBg, j); }
+          for (int j = 0; j < kK; ++j) { ccx[j * kM] = bx[j * kM]; ccg[j * kM] = bg[j * kM]; }
           clp = blp; cen = ben;
         }
         float s2[2] = {0.f, 0.f};
         {
-          uint32_t rt[kK];
-          tmem_ld26(rho_addr, rt);
+          float* rh = sv(kVRho);
+          const float* om = sv(kVOm);
+          for_chunks([&](auto off, auto nn) {
+            constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+            uint32_t rt[N];
+            tmem_ld<N>(rho_addr + OFF, rt);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < kK; ++j) {
-            const float rr = PB2_SCR(kVRho, j) + __uint_as_float(rt[j]);
-            PB2_SCR(kVRho, j) = rr;
-            s2[0] = fmaf(rr, m[j], s2[0]);
-            s2[1] = fmaf(rr, PB2_SCR(kVOm, j), s2[1]);
-          }
+            for (int j = 0; j < N; ++j) {
+              const float rr = rh[(OFF + j) * kM] + __uint_as_float(rt[j]);
+              rh[(OFF + j) * kM] = rr;
+              s2[0] = fmaf(rr, m[OFF + j], s2[0]);
+              s2[1] = fmaf(rr, om[(OFF + j) * kM], s2[1]);
+            }
+          });
         }
         cx.reduce<2>(s2);
         nleap += n;
@@ -373,8 +411,11 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         any_cont = __syncthreads_or(cont ? 1 : 0);       // nuts.py:404-407
       }
       // ---- results (nuts.py:424-445); the next state is the trajectory candidate
+      {
+        const float *ccx = sv(kVCx), *ccg = sv(kVCg);
 #pragma unroll
-      for (int j = 0; j < kK; ++j) { x[j] = PB2_SCR(kVCx, j); g[j] = PB2_SCR(kVCg, j); }
+        for (int j = 0; j < kK; ++j) { x[j] = ccx[j * kM]; g[j] = ccg[j * kM]; }
+      }
       lp = clp;
       const int leap = nleap * p.unrolled;
       nleap_total += (unsigned long long)leap;
@@ -406,7 +447,6 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   }
   cx.finish();
 }
-#undef PB2_SCR
 
 bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p) {
   if (ctx->dense_variant == 1) return false;                       // PB2_DENSE_VARIANT=1: force warp-per-chain

@@ -479,3 +479,82 @@ def test_ess_iid_is_n(tfp):
   np.testing.assert_allclose(got, 5000., rtol=0.1)
   got = tfp.mcmc.effective_sample_size(t(x), filter_threshold=None, filter_beyond_positive_pairs=True).cpu().numpy()
   np.testing.assert_allclose(got, 5000., rtol=0.25)
+
+
+# ------------------------------------------------------------------ tcgen05 tile kernels (dense Gaussian, B >= 256)
+def _dense100_state(B, seed=0):
+  import probability_b200 as tfp_
+  tg = tfp_.targets.IllConditionedGaussian()
+  rng = np.random.default_rng(seed)
+  L = np.linalg.cholesky(tg.covariance)
+  x0 = (rng.standard_normal((B, 100)) @ L.T).astype(np.float32)
+  return tg, otargets.DenseGaussian(tg.precision, tg.log_normalizer), x0
+
+
+def test_tensor_core_logp_grad_is_fp32_accurate(tfp):
+  """pb2_dense_logp_grad_tc (tcgen05, 3xTF32): as close to float64 as the FP32-FMA kernel."""
+  from probability_b200 import _lib
+  tg, o32, x0 = _dense100_state(300)
+  ctx = _lib.Context.get(dev()); ctx.bind_stream()
+  xt = t(x0)
+  lp = torch.empty(300, device=dev()); g = torch.empty(300, 100, device=dev())
+  _lib.check(ctx.lib.pb2_dense_logp_grad_tc(ctx.handle, tg.handle(ctx), 300, _lib.ptr(xt), _lib.ptr(lp), _lib.ptr(g)),
+             ctx.handle)
+  g64 = -(x0.astype(np.float64) @ tg.precision.astype(np.float64))
+  lp64 = 0.5 * np.sum(x0 * g64, 1) + tg.log_normalizer
+  lp32, g32 = o32.logp_grad(x0)
+  scale = np.abs(g64).max(1, keepdims=True)
+  assert np.max(np.abs(g.cpu().numpy() - g64) / scale) < 3 * max(np.max(np.abs(g32 - g64) / scale), 1e-6)
+  assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 3 * max(np.max(np.abs(lp32 - lp64) / np.abs(lp64)), 1e-6)
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_tile_hmc_matches_oracle(tfp, variant):
+  from probability_b200 import _lib
+  tg, o32, x0 = _dense100_state(300)
+  ctx = _lib.Context.get(dev())
+  ctx.set_int('dense_variant', variant)
+  try:
+    k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.5, num_leapfrog_steps=5)
+    seed = orng.key(4)
+    s, r = k.one_step(t(x0), k.bootstrap_results(t(x0)), seed=seed)
+    lp0, g0 = o32.logp_grad(x0)
+    ref = omcmc.hmc_one_step(o32, x0, lp0, g0, 0.5, 5, seed)
+    acc = r.is_accepted.cpu().numpy()
+    agree = acc == ref['is_accepted']
+    assert agree.mean() > 0.98
+    np.testing.assert_allclose(r.proposed_results.initial_momentum.cpu().numpy(), ref['initial_momentum'], atol=1e-6)
+    np.testing.assert_allclose(s.cpu().numpy()[agree], ref['state'][agree], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(r.log_accept_ratio.cpu().numpy(), ref['log_accept_ratio'], atol=2e-2)
+  finally:
+    ctx.set_int('dense_variant', 0)
+
+
+@pytest.mark.parametrize('depth,eps', [(3, 0.3), (6, 0.5)])
+def test_tile_nuts_matches_oracle_and_warp_kernel(tfp, depth, eps):
+  """The lock-step 128-chain tile kernel IS the reference's batched algorithm: same trees as the
+  oracle, and as the warp-per-chain kernel (per-chain early exit)."""
+  from probability_b200 import _lib
+  tg, o32, x0 = _dense100_state(300)
+  ctx = _lib.Context.get(dev())
+  k = tfp.mcmc.NoUTurnSampler(tg, step_size=eps, max_tree_depth=depth)
+  seed = orng.key(4)
+  outs = {}
+  try:
+    for variant in (0, 1):
+      ctx.set_int('dense_variant', variant)
+      s, r = k.one_step(t(x0), k.bootstrap_results(t(x0)), seed=seed)
+      outs[variant] = (s.cpu().numpy(), r)
+  finally:
+    ctx.set_int('dense_variant', 0)
+  lp0, g0 = o32.logp_grad(x0)
+  ref = omcmc.nuts_one_step(o32, x0, lp0, g0, eps, seed, max_tree_depth=depth)
+  for variant in (0, 1):
+    s, r = outs[variant]
+    same = r.leapfrogs_taken.cpu().numpy() == ref['leapfrogs_taken']
+    assert same.mean() >= 0.97
+    close = np.isclose(s, ref['state'], rtol=2e-3, atol=2e-3).all(1)
+    assert close[same].mean() >= 0.97
+    for f in ('is_accepted', 'reach_max_depth', 'has_divergence'):
+      assert (getattr(r, f).cpu().numpy() == ref[f])[same & close].all(), f
+  assert (outs[0][1].leapfrogs_taken == outs[1][1].leapfrogs_taken).float().mean() > 0.97
