@@ -4,6 +4,8 @@
 // All chains of a tile advance in lock-step; each leapfrog's gradient is one 3xTF32 tensor-core
 // contraction (pb2_tile.cuh).  Same seeds, same counters, same decisions as the warp-per-chain
 // kernels and the oracle (the uint32 streams are identical; floats agree to rounding).
+#include <cstdio>
+#include <cstdlib>
 #include "pb2_tile.cuh"
 
 namespace pb2 {
@@ -448,6 +450,10 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   cx.finish();
 }
 
+}  // namespace pb2
+#include "pb2_tile_sched.cuh"
+namespace pb2 {
+
 bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p) {
   if (ctx->dense_variant == 1) return false;                       // PB2_DENSE_VARIANT=1: force warp-per-chain
   if (tgt->kind != PB2_TARGET_DENSE_GAUSSIAN) return false;
@@ -469,6 +475,53 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     tile_hmc_kernel<<<grid, kThreads, smem, ctx->stream>>>(p, tp);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "tile_hmc_kernel");
+  }
+  // fused multi-transition NUTS runs: chains re-grouped at doubling boundaries (pb2_tile_sched.cuh)
+  const int kS0 = 5;
+  if (mode == kModeNUTS && ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 &&
+      p.max_depth > kS0) {
+    const int sgrid = ctx->num_sms;
+    const size_t scr_bytes = (size_t)sgrid * (2 + 2 * p.max_depth) * kKP * kM * sizeof(float);
+    const size_t vec_bytes = (size_t)p.B * kRecVecs * kKP * sizeof(float);
+    const size_t scal_bytes = (size_t)p.B * kRecScal * sizeof(float);
+    const size_t need = scr_bytes + vec_bytes + scal_bytes + (size_t)p.B * sizeof(int);
+    if (need > ctx->ckpt_bytes) {
+      if (ctx->d_ckpt) cudaFree(ctx->d_ckpt);
+      ctx->d_ckpt = nullptr;
+      ctx->ckpt_bytes = 0;
+      if (int rc = check_cuda(ctx, cudaMalloc(&ctx->d_ckpt, need), "cudaMalloc(tile scheduler)")) return rc;
+      ctx->ckpt_bytes = need;
+    }
+    unsigned char* base = reinterpret_cast<unsigned char*>(ctx->d_ckpt);
+    SchedParams sp;
+    sp.rec_vec = reinterpret_cast<float*>(base + scr_bytes);
+    sp.rec_scal = reinterpret_cast<float*>(base + scr_bytes + vec_bytes);
+    sp.ready = reinterpret_cast<int*>(base + scr_bytes + vec_bytes + scal_bytes);
+    sp.s0 = kS0;
+    sp.stats = nullptr;
+    static unsigned long long* d_stats = nullptr;
+    if (getenv("PB2_SCHED_STATS")) {
+      if (!d_stats) cudaMalloc(&d_stats, 32 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), ctx->stream);
+      sp.stats = d_stats;
+    }
+    tile_sched_init_kernel<<<(p.B + 255) / 256, 256, 0, ctx->stream>>>(sp.ready, sp.rec_scal, p.B, p.t0);
+    if (int rc = check_cuda(ctx, cudaFuncSetAttribute(tile_nuts_sched_kernel,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(tile_nuts_sched)"))
+      return rc;
+    tile_nuts_sched_kernel<<<sgrid, kThreads, smem, ctx->stream>>>(p, tp, sp, ctx->d_ckpt);
+    ctx->launches += 2;
+    if (sp.stats) {
+      unsigned long long h[32];
+      cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[sched] tasks %llu chains %llu (fill %.1f) ticks %llu idle-polls %llu | per class tasks:", h[0], h[1],
+              h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3]);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu(%.0f)", h[8 + k], h[8 + k] ? (double)h[20 + k] / h[8 + k] : 0.0);
+      fprintf(stderr, "\n");
+    }
+    return check_cuda(ctx, cudaGetLastError(), "tile_nuts_sched_kernel");
   }
   if (mode == kModeNUTS) {
     const size_t per_cta = (size_t)(kVCk + 2 * p.max_depth) * kKP * kM * sizeof(float);

@@ -1,0 +1,434 @@
+// tile_nuts_sched_kernel: the tcgen05 tile NUTS kernel with chains re-grouped at DOUBLING boundaries.
+//
+// The lock-step tile kernel (tile_nuts_kernel) makes all 128 chains of a tile wait for the tile's
+// deepest tree (measured utilisation 0.27 on the 100-d ill-conditioned Gaussian: mean 276 of max
+// 1023 leapfrogs).  Here the unit of work is a TASK = one tree doubling (2^it leaves, identical for
+// every chain of the task):
+//   class 0      : start a transition (momentum, H0, ...) and run doublings it = 0 .. s0-1
+//   class k >= 1 : doubling it = s0 + k - 1
+// Persistent CTAs repeatedly (1) histogram the per-chain `ready` words, (2) claim up to 128 chains of
+// one class with atomicCAS, (3) run the task in lock-step exactly like tile_nuts_kernel, (4) publish
+// each chain's next class (or finish its transition, emit the traced results and start the next one).
+// A chain's results do not depend on which tile/CTA ran its tasks: every random number is a function
+// of (step seed, global chain index) and all per-chain reductions have a fixed order.
+// Chain-major records hold what survives a doubling boundary (both trajectory ends, the trajectory
+// candidate, rho and the scalars); the subtree candidate and the checkpoint stores are dead at a
+// boundary and stay in the CTA's scratch.
+#pragma once
+#include "pb2_tile.cuh"
+
+namespace pb2 {
+using namespace tile;
+
+enum { kRSx = 0, kRSm, kRSg, kROx, kROm, kROg, kRCx, kRCg, kRRho, kRecVecs };
+enum { kSLp = 0, kSH0, kSSlp, kSOlp, kSClp, kSCen, kSCw, kSEsum, kSNleap, kSFlags, kST, kSNleapTot, kRecScal = 16 };
+constexpr int kReadyRunning = -1, kReadyDone = 99;
+
+struct SchedParams {
+  float* rec_vec;    // [B][kRecVecs][kKP]
+  float* rec_scal;   // [B][kRecScal]
+  int* ready;        // [B]
+  int s0;            // doublings merged into the start task
+  unsigned long long* stats;   // optional [32]: tasks, claimed chains, ticks, idle polls, per-class tasks @8+
+};
+
+__global__ void tile_sched_init_kernel(int* ready, float* rec_scal, int B, int t0) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B) return;
+  ready[c] = 0;
+  rec_scal[(size_t)c * kRecScal + kST] = __int_as_float(t0);
+  rec_scal[(size_t)c * kRecScal + kSNleapTot] = __int_as_float(0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const SchedParams sp,
+                       float* __restrict__ scratch_all) {
+  extern __shared__ __align__(128) unsigned char planes[];
+  __shared__ Shared sh;
+  __shared__ float lu[4][kM];
+  __shared__ int hist[16];
+  __shared__ int ids[kM];
+  __shared__ int n_claimed, n_done, sel_cls;
+  Ctx cx;
+  cx.init(&sh, planes, tp.P, tp.loc, tp.D);
+  const int D = tp.D;
+  const int tid = threadIdx.x;
+  constexpr size_t kVS = (size_t)kKP * kM;
+  // CTA scratch: subtree candidate (x, g) + checkpoint stores, [vector][dim][lane]
+  enum { kTBx = 0, kTBg = 1, kTCk = 2 };
+  const int nvec = kTCk + 2 * p.max_depth;
+  float* const scr_t = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM + cx.cl;
+  auto sv = [&](int v) -> float* { return scr_t + (size_t)v * kVS; };
+  const float* lc = sh.loc + kK * cx.slice;
+  const uint32_t rho_addr = cx.lane_addr + kColRho + kK * cx.slice;
+  const int nclass = 1 + max(0, p.max_depth - sp.s0);
+  unsigned gt = 0;
+  int patience = 0;                 // consecutive polls without a full tile (uniform across the CTA)
+  constexpr int kPatience = 24;     // ~0.3 ms of polling before a partially filled tile is accepted
+  const int scan0 = (int)(((long long)blockIdx.x * p.B) / gridDim.x);   // de-correlate the CTAs' scans
+
+  while (true) {
+    // ------------------------------------------------------------ (1) what is ready?
+    __syncthreads();   // everybody is done reading the shared scheduling words of the previous round
+    if (tid < 16) hist[tid] = 0;
+    if (tid == 0) { n_claimed = 0; n_done = 0; }
+    __syncthreads();
+    {
+      int loc_done = 0;
+      for (int i = tid; i < p.B; i += kThreads) {
+        const int rd = *(volatile int*)(sp.ready + i);
+        if (rd == kReadyDone) loc_done++;
+        else if (rd >= 0 && rd < 16) atomicAdd(&hist[rd], 1);
+      }
+      if (loc_done) atomicAdd(&n_done, loc_done);
+    }
+    __syncthreads();
+    if (n_done == p.B) break;
+    if (tid == 0) {
+      // policy: a FULL tile of the deepest class first (deep tasks are long: running them partially filled is
+      // what wastes the machine).  Without a full tile: wait for producers for a while (patience), then take
+      // the fullest class -- immediately if nothing is running anywhere (end of the run).
+      int best = -1, best_n = 0, n_ready = 0;
+      for (int k = 0; k < nclass; ++k) n_ready += hist[k];
+      for (int k = nclass - 1; k >= 0; --k)
+        if (hist[k] >= kM) { best = k; best_n = hist[k]; break; }
+      if (best < 0) {
+        const int n_running = p.B - n_done - n_ready;
+        if (n_running == 0 || patience >= kPatience) {
+          for (int k = 0; k < nclass; ++k)
+            if (hist[k] > best_n) { best = k; best_n = hist[k]; }
+        }
+      }
+      sel_cls = best;
+    }
+    __syncthreads();
+    const int cls = sel_cls;
+    if (cls < 0) {
+      if (sp.stats && tid == 0) atomicAdd(sp.stats + 3, 1ull);
+      patience++;
+      __nanosleep(10000);
+      continue;
+    }
+    // ------------------------------------------------------------ (2) claim up to 128 chains of that class
+    for (int i0 = tid; i0 < p.B; i0 += kThreads) {
+      if (*(volatile int*)&n_claimed >= kM) break;
+      int i = i0 + scan0;
+      if (i >= p.B) i -= p.B;
+      if (*(volatile int*)(sp.ready + i) == cls && atomicCAS(sp.ready + i, cls, kReadyRunning) == cls) {
+        const int slot = atomicAdd(&n_claimed, 1);
+        if (slot < kM) ids[slot] = i;
+        else atomicExch(sp.ready + i, cls);          // tile is full: give it back
+      }
+    }
+    __syncthreads();
+    const int ntask = min(n_claimed, kM);
+    if (ntask == 0) continue;
+    patience = 0;
+    if (sp.stats && tid == 0) {
+      atomicAdd(sp.stats + 0, 1ull);
+      atomicAdd(sp.stats + 1, (unsigned long long)ntask);
+      atomicAdd(sp.stats + 8 + cls, 1ull);
+      atomicAdd(sp.stats + 20 + cls, (unsigned long long)ntask);
+    }
+    const unsigned gt_begin = gt;
+    __threadfence();
+    // ------------------------------------------------------------ (3) run the task in lock-step
+    const bool live = cx.cl < ntask;
+    const int c = live ? ids[cx.cl] : 0;
+    const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)c;
+    float* const rec = sp.rec_vec + (size_t)c * kRecVecs * kKP + kK * cx.slice;   // element j of vector v: rec[v*kKP + j]
+    float* const rs = sp.rec_scal + (size_t)c * kRecScal;
+    const int t = live ? __float_as_int(rs[kST]) : p.t0;
+    const float eps_abs = p.step_kind == 0 ? p.step[0] : (live ? p.step[c] : 0.f);
+    const uint32_t* sk = p.sched + (size_t)(t - p.t_sched0) * p.sched_stride;
+    const uint32_t* hdr = sk + 2 * p.n_parts;
+    const uint32_t* ku = hdr + 6 * p.max_depth;
+    float x[kK], m[kK], g[kK];
+    float lp, H0, slp, olp, clp, cen, cw, esum;
+    int nleap;
+    bool cont, notdiv, accepted, s_is_right;
+    int it_begin, it_end;
+    if (cls == 0) {
+      // ---- _start_trajectory_batched (nuts.py:512-539)
+      tile_load(p.x, c, D, cx.slice, live, x);
+      tile_load(p.g, c, D, cx.slice, live, g);
+      lp = live ? p.lp[c] : 0.f;
+      float s1[1] = {0.f};
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const int d = kK * cx.slice + j;
+        const float mm = (live && d < D) ? tile_momentum(p, sk, cg, d) : 0.f;
+        m[j] = mm;
+        s1[0] = fmaf(mm, mm, s1[0]);
+        if (live) {
+          rec[kROx * kKP + j] = x[j]; rec[kROm * kKP + j] = mm; rec[kROg * kKP + j] = g[j];
+          rec[kRCx * kKP + j] = x[j]; rec[kRCg * kKP + j] = g[j];
+          rec[kRRho * kKP + j] = mm;
+        }
+      }
+      cx.reduce<1>(s1);
+      H0 = lp - 0.5f * s1[0];
+      slp = lp; olp = lp; clp = lp; cen = H0; cw = 0.f; esum = 0.f;
+      nleap = 0;
+      cont = live; notdiv = true; accepted = false; s_is_right = true;
+      it_begin = 0;
+      it_end = min(sp.s0, p.max_depth);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        x[j] = live ? rec[kRSx * kKP + j] : 0.f;
+        m[j] = live ? rec[kRSm * kKP + j] : 0.f;
+        g[j] = live ? rec[kRSg * kKP + j] : 0.f;
+      }
+      lp = live ? rs[kSLp] : 0.f;  H0 = live ? rs[kSH0] : 0.f;  slp = live ? rs[kSSlp] : 0.f;
+      olp = live ? rs[kSOlp] : 0.f;  clp = live ? rs[kSClp] : 0.f;  cen = live ? rs[kSCen] : 0.f;
+      cw = live ? rs[kSCw] : 0.f;  esum = live ? rs[kSEsum] : 0.f;
+      nleap = live ? __float_as_int(rs[kSNleap]) : 0;
+      const int fl = live ? __float_as_int(rs[kSFlags]) : 0;
+      cont = live; notdiv = (fl & 2) != 0; accepted = (fl & 4) != 0; s_is_right = (fl & 8) != 0;
+      it_begin = sp.s0 + cls - 1;
+      it_end = it_begin + 1;
+    }
+    int any_cont = __syncthreads_or(cont ? 1 : 0);
+#pragma unroll 1
+    for (int it = it_begin; it < it_end && any_cont; ++it) {
+      Key kd{hdr[6 * it], hdr[6 * it + 1]}, kac{hdr[6 * it + 2], hdr[6 * it + 3]};
+      const bool dir = (bits_at(kd, cg, (uint64_t)p.B_global, p.layout) & 1u) != 0;
+      const float lacc = log1pf(-uniform_from_bits(bits_at(kac, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
+      if (live && dir != s_is_right) {
+#pragma unroll
+        for (int j = 0; j < kK; ++j) {
+          float a;
+          a = rec[kROx * kKP + j]; rec[kROx * kKP + j] = x[j]; x[j] = a;
+          a = rec[kROm * kKP + j]; rec[kROm * kKP + j] = m[j]; m[j] = a;
+          a = rec[kROg * kKP + j]; rec[kROg * kKP + j] = g[j]; g[j] = a;
+        }
+        const float a = slp; slp = olp; olp = a;
+        s_is_right = dir;
+      }
+      const float eps = dir ? eps_abs : -eps_abs;
+      const float heps = 0.5f * eps;
+      {
+        float *bx = sv(kTBx), *bg = sv(kTBg);
+#pragma unroll
+        for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
+        for_chunks([&](auto off, auto n) {
+          constexpr int OFF = decltype(off)::value, N = decltype(n)::value;
+          uint32_t z[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) z[j] = 0u;
+          tmem_st<N>(rho_addr + OFF, z);
+        });
+      }
+      float blp = slp, ben = slp, bw = -INFINITY;
+      int n = 0;
+      bool c_prev = cont, nd = notdiv;
+      float esum_sub = 0.f;
+      const int nsteps = 1 << it;
+      const uint32_t* kud = ku + 2 * (nsteps - 1);
+#pragma unroll 1
+      for (int i = 0; i < nsteps; ++i, ++gt) {
+        if ((i & 3) == 0 && i + cx.slice < nsteps) {
+          Key kk{kud[2 * (i + cx.slice)], kud[2 * (i + cx.slice) + 1]};
+          lu[cx.slice][cx.cl] = log1pf(-uniform_from_bits(bits_at(kk, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
+        }
+#pragma unroll
+        for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
+        bool stop = false;
+#pragma unroll 1
+        for (int l = 0; l < p.unrolled; ++l) {
+#pragma unroll
+          for (int j = 0; j < kK; ++j) x[j] = x[j] + eps * m[j];
+          cx.stage_a(x);
+          cx.contract();
+          if (l == 0) {
+            if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
+            if (tid == 0) sh.flags[(gt + 1) & 3] = 0;
+          }
+          if (stop) break;
+          cx.load_d(g);
+#pragma unroll
+          for (int j = 0; j < kK; ++j) m[j] = m[j] + eps * g[j];
+        }
+        if (stop) break;
+#pragma unroll
+        for (int j = 0; j < kK; ++j) m[j] = m[j] - heps * g[j];
+        n += c_prev ? 1 : 0;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        const int pc = __popc(i);
+        const bool odd = (i & 1) != 0;
+        const int k0 = pc - (__ffs(~i) - 1);
+        float* ckm_w = sv(kTCk + pc);
+        float* ckr_w = sv(kTCk + p.max_depth + pc);
+        const float* ckm_r = sv(kTCk + k0);
+        const float* ckr_r = sv(kTCk + p.max_depth + k0);
+        for_chunks([&](auto off, auto nn) {
+          constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+          uint32_t rt[N];
+          tmem_ld<N>(rho_addr + OFF, rt);
+          tmem_wait_ld();
+          if (!odd) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              ckm_w[(OFF + j) * kM] = m[OFF + j];
+              ckr_w[(OFF + j) * kM] = __uint_as_float(rt[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            const float rn = __uint_as_float(rt[j]) + m[OFF + j];
+            rt[j] = __float_as_uint(rn);
+            s4[0] = fmaf(x[OFF + j] - lc[OFF + j], g[OFF + j], s4[0]);
+            s4[1] = fmaf(m[OFF + j], m[OFF + j], s4[1]);
+          }
+          tmem_st<N>(rho_addr + OFF, rt);
+          if (odd) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              const float diff = __uint_as_float(rt[j]) - ckr_r[(OFF + j) * kM];
+              s4[2] = fmaf(diff, ckm_r[(OFF + j) * kM], s4[2]);
+              s4[3] = fmaf(diff, m[OFF + j], s4[3]);
+            }
+          }
+        });
+        cx.reduce<4>(s4);
+        slp = fmaf(0.5f, s4[0], tp.lognorm);
+        bool ok = true;
+        if (odd) {
+          ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
+#pragma unroll 1
+          for (int k = k0 + 1; k < pc; ++k) {
+            const float* km = sv(kTCk + k);
+            const float* kr = sv(kTCk + p.max_depth + k);
+            float s2[2] = {0.f, 0.f};
+            for_chunks([&](auto off, auto nn) {
+              constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+              uint32_t rt[N];
+              tmem_ld<N>(rho_addr + OFF, rt);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < N; ++j) {
+                const float diff = __uint_as_float(rt[j]) - kr[(OFF + j) * kM];
+                s2[0] = fmaf(diff, km[(OFF + j) * kM], s2[0]);
+                s2[1] = fmaf(diff, m[OFF + j], s2[1]);
+              }
+            });
+            cx.reduce<2>(s2);
+            ok = ok && (s2[0] >= 0.f) && (s2[1] >= 0.f);
+          }
+        }
+        float en = slp - 0.5f * s4[1];
+        en = isnan(en) ? -INFINITY : en;
+        const float dH = en - H0;
+        const bool nd_i = (-dH) < p.max_energy_diff;
+        const float w_new = log_add_exp(bw, dH);
+        const bool take = lu[i & 3][cx.cl] <= (dH - w_new);
+        if (take) {
+          float *bx = sv(kTBx), *bg = sv(kTBg);
+#pragma unroll
+          for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
+          blp = slp; ben = en;
+        }
+        bw = w_new;
+        const bool c_now = nd_i && c_prev;
+        if (c_now) esum_sub += expf(fminf(dH, 0.f));
+        nd = nd && (c_prev ? nd_i : true);
+        c_prev = ok && c_now;
+        if (c_prev) sh.flags[gt & 3] = 1;
+      }
+      const bool cont_f = c_prev;
+      esum = esum_sub + esum;
+      const float tw = cont_f ? bw : -INFINITY;
+      const float wsum = log_add_exp(tw, cw);
+      float thr = tw - cw;
+      thr = isnan(thr) ? 0.f : thr;
+      const bool swap = (lacc <= thr) && cont_f;
+      cw = wsum;
+      if (swap && live) {
+        const float *bx = sv(kTBx), *bg = sv(kTBg);
+#pragma unroll
+        for (int j = 0; j < kK; ++j) { rec[kRCx * kKP + j] = bx[j * kM]; rec[kRCg * kKP + j] = bg[j * kM]; }
+        clp = blp; cen = ben;
+      }
+      float s2[2] = {0.f, 0.f};
+      for_chunks([&](auto off, auto nn) {
+        constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+        uint32_t rt[N];
+        tmem_ld<N>(rho_addr + OFF, rt);
+        tmem_wait_ld();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            const float rr = rec[kRRho * kKP + OFF + j] + __uint_as_float(rt[j]);
+            rec[kRRho * kKP + OFF + j] = rr;
+            s2[0] = fmaf(rr, m[OFF + j], s2[0]);
+            s2[1] = fmaf(rr, rec[kROm * kKP + OFF + j], s2[1]);
+          }
+        }
+      });
+      cx.reduce<2>(s2);
+      nleap += n;
+      accepted = accepted || swap;
+      notdiv = nd;
+      cont = cont_f && (s2[0] >= 0.f) && (s2[1] >= 0.f);
+      any_cont = __syncthreads_or(cont ? 1 : 0);
+    }
+    if (sp.stats && tid == 0) atomicAdd(sp.stats + 2, (unsigned long long)(gt - gt_begin));
+    // ------------------------------------------------------------ (4) publish: finished transition or next doubling
+    const bool finished = !cont || it_end >= p.max_depth;
+    int next_ready = kReadyRunning;
+    if (live) {
+      if (finished) {
+        float fx[kK], fg[kK];
+#pragma unroll
+        for (int j = 0; j < kK; ++j) { fx[j] = rec[kRCx * kKP + j]; fg[j] = rec[kRCg * kKP + j]; }
+        const int leap = nleap * p.unrolled;
+        const float lar = logf(esum / (float)nleap);
+        const int r = tile_result_index(p, t);
+        tile_store(p.x, 0, p.B, c, D, cx.slice, true, fx);
+        tile_store(p.g, 0, p.B, c, D, cx.slice, true, fg);
+        if (r >= 0) {
+          const Trace& tr = p.tr;
+          if (tr.states) tile_store(tr.states, r, p.B, c, D, cx.slice, true, fx);
+          if (tr.grads) tile_store(tr.grads, r, p.B, c, D, cx.slice, true, fg);
+        }
+        if (cx.slice == 0) {
+          p.lp[c] = clp;
+          if (p.leapfrog_total) p.leapfrog_total[c] += (unsigned long long)leap;
+          if (r >= 0) {
+            const Trace& tr = p.tr;
+            const size_t o = (size_t)r * p.B + c;
+            if (tr.target_log_prob) tr.target_log_prob[o] = clp;
+            if (tr.log_accept_ratio) tr.log_accept_ratio[o] = lar;
+            if (tr.is_accepted) tr.is_accepted[o] = accepted ? 1 : 0;
+            if (tr.leapfrogs_taken) tr.leapfrogs_taken[o] = leap;
+            if (tr.has_divergence) tr.has_divergence[o] = notdiv ? 0 : 1;
+            if (tr.reach_max_depth) tr.reach_max_depth[o] = cont ? 1 : 0;
+            if (tr.energy) tr.energy[o] = cen;
+            if (tr.step_size && c == 0 && p.step_kind == 0) tr.step_size[r] = p.step[0];
+          }
+          rs[kST] = __int_as_float(t + 1);
+        }
+        next_ready = (t + 1 < p.t1) ? 0 : kReadyDone;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kK; ++j) {
+          rec[kRSx * kKP + j] = x[j]; rec[kRSm * kKP + j] = m[j]; rec[kRSg * kKP + j] = g[j];
+        }
+        if (cx.slice == 0) {
+          rs[kSLp] = lp; rs[kSH0] = H0; rs[kSSlp] = slp; rs[kSOlp] = olp; rs[kSClp] = clp; rs[kSCen] = cen;
+          rs[kSCw] = cw; rs[kSEsum] = esum;
+          rs[kSNleap] = __int_as_float(nleap);
+          rs[kSFlags] = __int_as_float((notdiv ? 2 : 0) | (accepted ? 4 : 0) | (s_is_right ? 8 : 0));
+        }
+        next_ready = (cls == 0) ? 1 : cls + 1;
+      }
+    }
+    __threadfence();
+    __syncthreads();   // all four slices of every chain have written their part of the record
+    if (live && cx.slice == 0) atomicExch(sp.ready + c, next_ready);
+  }
+  cx.finish();
+}
+
+}  // namespace pb2
