@@ -268,6 +268,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
 #pragma unroll
           for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
           bool stop = false;
+          float lu_i = 0.f;
 #pragma unroll 1
           for (int l = 0; l < p.unrolled; ++l) {
 #pragma unroll
@@ -275,6 +276,8 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
             cx.stage_a(x);
             cx.contract();
             if (l == 0) {
+              // read before the next barrier: a faster slice may overwrite lu[] for the next 4 leaves after it
+              lu_i = lu[i & 3][cx.cl];
               // nuts.py:759 reduce_any(continue_tree): flag raised at the end of the previous leaf; leaving
               // mid-leaf is harmless because no chain of the tile continues (ends/candidates are final)
               if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
@@ -358,7 +361,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
           const float dH = en - H0;
           const bool nd_i = (-dH) < p.max_energy_diff;   // :880
           const float w_new = log_add_exp(bw, dH);       // :881-883
-          const bool take = lu[i & 3][cx.cl] <= (dH - w_new);   // :897-901
+          const bool take = lu_i <= (dH - w_new);   // :897-901
           if (take) {
             float *bx = sv(kVBx), *bg = sv(kVBg);
 #pragma unroll
@@ -480,7 +483,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
   const int kS0 = 5;
   if (mode == kModeNUTS && ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 &&
       p.max_depth > kS0) {
-    const int sgrid = ctx->num_sms;
+    const int sgrid = getenv("PB2_SCHED_GRID") ? atoi(getenv("PB2_SCHED_GRID")) : ctx->num_sms;
     const size_t scr_bytes = (size_t)sgrid * (2 + 2 * p.max_depth) * kKP * kM * sizeof(float);
     const size_t vec_bytes = (size_t)p.B * kRecVecs * kKP * sizeof(float);
     const size_t scal_bytes = (size_t)p.B * kRecScal * sizeof(float);
@@ -498,6 +501,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     sp.rec_scal = reinterpret_cast<float*>(base + scr_bytes + vec_bytes);
     sp.ready = reinterpret_cast<int*>(base + scr_bytes + vec_bytes + scal_bytes);
     sp.s0 = kS0;
+    sp.patience = getenv("PB2_SCHED_PATIENCE") ? atoi(getenv("PB2_SCHED_PATIENCE")) : 24;
     sp.stats = nullptr;
     static unsigned long long* d_stats = nullptr;
     if (getenv("PB2_SCHED_STATS")) {

@@ -29,6 +29,7 @@ struct SchedParams {
   float* rec_scal;   // [B][kRecScal]
   int* ready;        // [B]
   int s0;            // doublings merged into the start task
+  int patience;      // polls without a full tile before a partial tile is accepted
   unsigned long long* stats;   // optional [32]: tasks, claimed chains, ticks, idle polls, per-class tasks @8+
 };
 
@@ -64,7 +65,6 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
   const int nclass = 1 + max(0, p.max_depth - sp.s0);
   unsigned gt = 0;
   int patience = 0;                 // consecutive polls without a full tile (uniform across the CTA)
-  constexpr int kPatience = 24;     // ~0.3 ms of polling before a partially filled tile is accepted
   const int scan0 = (int)(((long long)blockIdx.x * p.B) / gridDim.x);   // de-correlate the CTAs' scans
 
   while (true) {
@@ -94,7 +94,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
         if (hist[k] >= kM) { best = k; best_n = hist[k]; break; }
       if (best < 0) {
         const int n_running = p.B - n_done - n_ready;
-        if (n_running == 0 || patience >= kPatience) {
+        if (n_running == 0 || patience >= sp.patience) {
           for (int k = 0; k < nclass; ++k)
             if (hist[k] > best_n) { best = k; best_n = hist[k]; }
         }
@@ -138,7 +138,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)c;
     float* const rec = sp.rec_vec + (size_t)c * kRecVecs * kKP + kK * cx.slice;   // element j of vector v: rec[v*kKP + j]
     float* const rs = sp.rec_scal + (size_t)c * kRecScal;
-    const int t = live ? __float_as_int(rs[kST]) : p.t0;
+    const int t = live ? __float_as_int(__ldcg(&rs[kST])) : p.t0;
     const float eps_abs = p.step_kind == 0 ? p.step[0] : (live ? p.step[c] : 0.f);
     const uint32_t* sk = p.sched + (size_t)(t - p.t_sched0) * p.sched_stride;
     const uint32_t* hdr = sk + 2 * p.n_parts;
@@ -150,9 +150,13 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     int it_begin, it_end;
     if (cls == 0) {
       // ---- _start_trajectory_batched (nuts.py:512-539)
-      tile_load(p.x, c, D, cx.slice, live, x);
-      tile_load(p.g, c, D, cx.slice, live, g);
-      lp = live ? p.lp[c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const bool in = live && (kK * cx.slice + j < D);
+        x[j] = in ? __ldcg(p.x + (size_t)c * D + kK * cx.slice + j) : 0.f;
+        g[j] = in ? __ldcg(p.g + (size_t)c * D + kK * cx.slice + j) : 0.f;
+      }
+      lp = live ? __ldcg(p.lp + c) : 0.f;
       float s1[1] = {0.f};
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
@@ -176,13 +180,13 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     } else {
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
-        x[j] = live ? rec[kRSx * kKP + j] : 0.f;
-        m[j] = live ? rec[kRSm * kKP + j] : 0.f;
-        g[j] = live ? rec[kRSg * kKP + j] : 0.f;
+        x[j] = live ? __ldcg(&rec[kRSx * kKP + j]) : 0.f;
+        m[j] = live ? __ldcg(&rec[kRSm * kKP + j]) : 0.f;
+        g[j] = live ? __ldcg(&rec[kRSg * kKP + j]) : 0.f;
       }
-      lp = live ? rs[kSLp] : 0.f;  H0 = live ? rs[kSH0] : 0.f;  slp = live ? rs[kSSlp] : 0.f;
-      olp = live ? rs[kSOlp] : 0.f;  clp = live ? rs[kSClp] : 0.f;  cen = live ? rs[kSCen] : 0.f;
-      cw = live ? rs[kSCw] : 0.f;  esum = live ? rs[kSEsum] : 0.f;
+      lp = live ? __ldcg(&rs[kSLp]) : 0.f;  H0 = live ? __ldcg(&rs[kSH0]) : 0.f;  slp = live ? __ldcg(&rs[kSSlp]) : 0.f;
+      olp = live ? __ldcg(&rs[kSOlp]) : 0.f;  clp = live ? __ldcg(&rs[kSClp]) : 0.f;  cen = live ? __ldcg(&rs[kSCen]) : 0.f;
+      cw = live ? __ldcg(&rs[kSCw]) : 0.f;  esum = live ? __ldcg(&rs[kSEsum]) : 0.f;
       nleap = live ? __float_as_int(rs[kSNleap]) : 0;
       const int fl = live ? __float_as_int(rs[kSFlags]) : 0;
       cont = live; notdiv = (fl & 2) != 0; accepted = (fl & 4) != 0; s_is_right = (fl & 8) != 0;
@@ -199,9 +203,9 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
 #pragma unroll
         for (int j = 0; j < kK; ++j) {
           float a;
-          a = rec[kROx * kKP + j]; rec[kROx * kKP + j] = x[j]; x[j] = a;
-          a = rec[kROm * kKP + j]; rec[kROm * kKP + j] = m[j]; m[j] = a;
-          a = rec[kROg * kKP + j]; rec[kROg * kKP + j] = g[j]; g[j] = a;
+          a = __ldcg(&rec[kROx * kKP + j]); rec[kROx * kKP + j] = x[j]; x[j] = a;
+          a = __ldcg(&rec[kROm * kKP + j]); rec[kROm * kKP + j] = m[j]; m[j] = a;
+          a = __ldcg(&rec[kROg * kKP + j]); rec[kROg * kKP + j] = g[j]; g[j] = a;
         }
         const float a = slp; slp = olp; olp = a;
         s_is_right = dir;
@@ -235,6 +239,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
 #pragma unroll
         for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
         bool stop = false;
+        float lu_i = 0.f;
 #pragma unroll 1
         for (int l = 0; l < p.unrolled; ++l) {
 #pragma unroll
@@ -242,6 +247,8 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
           cx.stage_a(x);
           cx.contract();
           if (l == 0) {
+            // read before the next barrier: a faster slice may overwrite lu[] for the next 4 leaves after it
+            lu_i = lu[i & 3][cx.cl];
             if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
             if (tid == 0) sh.flags[(gt + 1) & 3] = 0;
           }
@@ -322,7 +329,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
         const float dH = en - H0;
         const bool nd_i = (-dH) < p.max_energy_diff;
         const float w_new = log_add_exp(bw, dH);
-        const bool take = lu[i & 3][cx.cl] <= (dH - w_new);
+        const bool take = lu_i <= (dH - w_new);
         if (take) {
           float *bx = sv(kTBx), *bg = sv(kTBg);
 #pragma unroll
@@ -359,10 +366,10 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
         if (live) {
 #pragma unroll
           for (int j = 0; j < N; ++j) {
-            const float rr = rec[kRRho * kKP + OFF + j] + __uint_as_float(rt[j]);
+            const float rr = __ldcg(&rec[kRRho * kKP + OFF + j]) + __uint_as_float(rt[j]);
             rec[kRRho * kKP + OFF + j] = rr;
             s2[0] = fmaf(rr, m[OFF + j], s2[0]);
-            s2[1] = fmaf(rr, rec[kROm * kKP + OFF + j], s2[1]);
+            s2[1] = fmaf(rr, __ldcg(&rec[kROm * kKP + OFF + j]), s2[1]);
           }
         }
       });
@@ -381,7 +388,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
       if (finished) {
         float fx[kK], fg[kK];
 #pragma unroll
-        for (int j = 0; j < kK; ++j) { fx[j] = rec[kRCx * kKP + j]; fg[j] = rec[kRCg * kKP + j]; }
+        for (int j = 0; j < kK; ++j) { fx[j] = __ldcg(&rec[kRCx * kKP + j]); fg[j] = __ldcg(&rec[kRCg * kKP + j]); }
         const int leap = nleap * p.unrolled;
         const float lar = logf(esum / (float)nleap);
         const int r = tile_result_index(p, t);
