@@ -558,3 +558,33 @@ def test_tile_nuts_matches_oracle_and_warp_kernel(tfp, depth, eps):
     for f in ('is_accepted', 'reach_max_depth', 'has_divergence'):
       assert (getattr(r, f).cpu().numpy() == ref[f])[same & close].all(), f
   assert (outs[0][1].leapfrogs_taken == outs[1][1].leapfrogs_taken).float().mean() > 0.97
+
+
+@pytest.mark.parametrize('B,depth', [(1000, 7), (4096, 10)])
+def test_tile_nuts_doubling_scheduler_is_bit_identical_to_lockstep(tfp, B, depth):
+  """Multi-transition fused NUTS on the dense target runs the doubling-task scheduler
+  (pb2_tile_sched.cuh): chains are regrouped into 128-chain tiles per tree doubling.  Because every
+  random draw is keyed by (step seed, global chain index) and each chain's arithmetic is independent
+  of its tile mates, the result must equal the lock-step tile kernel's bit for bit -- and a ragged B
+  (1000 = 7 tiles + 104) exercises partially filled tiles."""
+  from probability_b200 import _lib
+  tg, _, x0 = _dense100_state(B, seed=3)
+  ctx = _lib.Context.get(dev())
+  k = tfp.mcmc.NoUTurnSampler(tg, step_size=0.74, max_tree_depth=depth)
+  fields = lambda _, kr: (kr.leapfrogs_taken, kr.is_accepted, kr.energy, kr.target_log_prob,
+                          kr.has_divergence, kr.reach_max_depth, kr.log_accept_ratio)
+  outs = {}
+  try:
+    for name, variant in (('sched', 0), ('lockstep', 3), ('sched_again', 0)):
+      ctx.set_int('dense_variant', variant)
+      res = tfp.mcmc.sample_chain(5, t(x0), kernel=k, trace_fn=fields, seed=7)
+      outs[name] = [res.all_states.cpu().numpy()] + [f.cpu().numpy() for f in res.trace]
+  finally:
+    ctx.set_int('dense_variant', 0)
+  for a, b in zip(outs['sched'], outs['lockstep']):
+    np.testing.assert_array_equal(a, b)
+  for a, b in zip(outs['sched'], outs['sched_again']):
+    np.testing.assert_array_equal(a, b)
+  assert np.isfinite(outs['sched'][0]).all() and np.isfinite(outs['sched'][3]).all()
+  lf = outs['sched'][1]
+  assert lf.min() >= 1 and lf.max() <= 2 ** depth - 1 and len(np.unique(lf)) > 3
