@@ -50,7 +50,8 @@ def build(force=False, verbose=False):
     if not os.path.exists(path):
       continue
     obj = os.path.join(OUT_DIR, src.replace('.cu', '.o'))
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj]
+    cmd = ([nvcc] + NVCC_FLAGS + os.environ.get('PB2_NVCC_EXTRA', '').split() +
+           (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj])
     procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     objs.append(obj)
   for cmd, pr in procs:

@@ -6,7 +6,7 @@
 // kernels and the oracle (the uint32 streams are identical; floats agree to rounding).
 #include <cstdio>
 #include <cstdlib>
-#include "pb2_tile.cuh"
+#include "pb2_tile_nuts.cuh"
 
 namespace pb2 {
 using namespace tile;
@@ -157,10 +157,11 @@ tile_hmc_kernel(const ChainParams p, const DenseGaussianParams tp) {
 // tile_nuts_kernel: NoUTurnSampler.one_step (tfp/mcmc/nuts.py:321-946) for a tile of 128 chains run
 // in LOCK-STEP, i.e. literally the reference's batched algorithm (shared doubling / leaf counters,
 // per-chain masks), which makes every leapfrog of the tile one tensor-core contraction.
-//   registers : moving trajectory end (x, m, g) of my 26-dim slice, per-chain scalars (replicated x4)
-//   TMEM      : rho_subtree (cumulative momentum of the subtree) next to the MMA operands
+//   registers : moving trajectory end (x, m) and rho_subtree of my 26-dim slice, per-chain scalars (replicated x4)
+//   TMEM      : g of the moving end (the contraction's accumulator) next to the MMA operands
+//   smem      : the previous leaf's checkpoint (pb2_tile_nuts.cuh)
 //   L2 scratch: other end, trajectory / subtree candidates, rho, the popcount-indexed checkpoint
-//               stores -- laid out [vector][dim][chain] so a warp's access is one 128 B line
+//               stores -- per-thread segments in the 128-bit layout of pb2_tile.cuh
 enum { kVOx = 0, kVOm, kVOg, kVCx, kVCg, kVBx, kVBg, kVRho, kVCk };   // checkpoints: kVCk + slot (m), + depth + slot (rho)
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -170,23 +171,34 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   __shared__ float lu[4][kM];   // log1p(-u) of the multinomial draws of 4 consecutive leaves
   Ctx cx;
   cx.init(&sh, planes, tp.P, tp.loc, tp.D);
+  Prof pf;
+  pf.init();
   const int D = tp.D;
+  const int cl = cx.cl;
   const int nvec = kVCk + 2 * p.max_depth;
-  constexpr size_t kVS = (size_t)kKP * kM;   // floats per scratch vector
-  // element j of scratch vector v of my (slice, chain): sv(v)[j * kM]
-  float* const scr_t = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM + cx.cl;
-  auto sv = [&](int v) -> float* { return scr_t + (size_t)v * kVS; };
-  const float* lc = sh.loc + kK * cx.slice;
-  const uint32_t rho_addr = cx.lane_addr + kColRho + kK * cx.slice;
+  // slice base of scratch vector v (the seg_* helpers add the chain)
+  float* const scr_s = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM;
+  auto sv = [&](int v) -> float* { return scr_s + (size_t)v * kVS; };
+  SubtreeArgs sa;
+  sa.unrolled = p.unrolled; sa.layout = p.layout; sa.b_global = (uint64_t)p.B_global;
+  sa.lognorm = tp.lognorm; sa.max_energy_diff = p.max_energy_diff;
+  sa.lc = sh.loc + kK * cx.slice;
+  sa.bx = sv(kVBx); sa.bg = sv(kVBg); sa.ck = sv(kVCk); sa.max_depth = p.max_depth;
+  sa.ckl = reinterpret_cast<float*>(planes + 2 * kPlaneBytes) + (size_t)(kK * cx.slice) * kM;
   const int ntiles = (p.B + kM - 1) / kM;
   unsigned gt = 0;   // global leaf counter (rotates the "somebody continues" flags)
   for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
-    const int c = tile_i * kM + cx.cl;
+    const int c = tile_i * kM + cl;
     const bool live = c < p.B;
     const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)c;
-    float x[kK], m[kK], g[kK];
+    sa.cg = cg;
+    float x[kK], m[kK], rho[kK];
     tile_load(p.x, c, D, cx.slice, live, x);
-    tile_load(p.g, c, D, cx.slice, live, g);
+    {
+      float g[kK];
+      tile_load(p.g, c, D, cx.slice, live, g);
+      cx.store_d(g);
+    }
     float lp = live ? p.lp[c] : 0.f;
     unsigned long long nleap_total = 0;
 #pragma unroll 1
@@ -199,20 +211,22 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
       // ---- _start_trajectory_batched (nuts.py:512-539): momentum, H0; both ends, candidate, rho
       float s1[1] = {0.f};
       {
-        float *ox = sv(kVOx), *om = sv(kVOm), *og = sv(kVOg), *ccx = sv(kVCx), *ccg = sv(kVCg), *rh = sv(kVRho);
+        float g[kK];
+        cx.load_d(g);
 #pragma unroll
         for (int j = 0; j < kK; ++j) {
           const int d = kK * cx.slice + j;
           const float mm = (live && d < D) ? tile_momentum(p, sk, cg, d) : 0.f;
           m[j] = mm;
           s1[0] = fmaf(mm, mm, s1[0]);
-          ox[j * kM] = x[j]; om[j * kM] = mm; og[j * kM] = g[j];
-          ccx[j * kM] = x[j]; ccg[j * kM] = g[j];
-          rh[j * kM] = mm;
         }
+        seg_st26(sv(kVOx), cl, x); seg_st26(sv(kVOm), cl, m); seg_st26(sv(kVOg), cl, g);
+        seg_st26(sv(kVCx), cl, x); seg_st26(sv(kVCg), cl, g);
+        seg_st26(sv(kVRho), cl, m);
       }
       cx.reduce<1>(s1);
       const float H0 = lp - 0.5f * s1[0];
+      sa.H0 = H0;
       float slp = lp, olp = lp, clp = lp, cen = H0, cw = 0.f;
       float esum = 0.f;
       int nleap = 0;
@@ -224,203 +238,77 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         Key kd{hdr[6 * it], hdr[6 * it + 1]}, kac{hdr[6 * it + 2], hdr[6 * it + 3]};
         const bool dir = (bits_at(kd, cg, (uint64_t)p.B_global, p.layout) & 1u) != 0;
         const float lacc = log1pf(-uniform_from_bits(bits_at(kac, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
-        if (dir != s_is_right) {   // registers must hold the end that is extended
-          float *ox = sv(kVOx), *om = sv(kVOm), *og = sv(kVOg);
-#pragma unroll
-          for (int j = 0; j < kK; ++j) {
-            float a;
-            a = ox[j * kM]; ox[j * kM] = x[j]; x[j] = a;
-            a = om[j * kM]; om[j * kM] = m[j]; m[j] = a;
-            a = og[j * kM]; og[j * kM] = g[j]; g[j] = a;
-          }
-          const float a = slp; slp = olp; olp = a;
-          s_is_right = dir;
-        }
-        const float eps = dir ? eps_abs : -eps_abs;
-        const float heps = 0.5f * eps;
-        // _build_sub_tree init (nuts.py:713-791)
+        // registers / D must hold the end that is extended; _build_sub_tree init (nuts.py:713-791)
         {
-          float *bx = sv(kVBx), *bg = sv(kVBg);
+          const bool sw = dir != s_is_right;
+          float g[kK];
+          cx.load_d(g);
+          if (sw) {
+            float o[kK];
+            seg_ld26(sv(kVOx), cl, o); seg_st26(sv(kVOx), cl, x);
 #pragma unroll
-          for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
-          for_chunks([&](auto off, auto n) {
-            constexpr int OFF = decltype(off)::value, N = decltype(n)::value;
-            uint32_t z[N];
+            for (int j = 0; j < kK; ++j) x[j] = o[j];
+            seg_ld26(sv(kVOm), cl, o); seg_st26(sv(kVOm), cl, m);
 #pragma unroll
-            for (int j = 0; j < N; ++j) z[j] = 0u;
-            tmem_st<N>(rho_addr + OFF, z);
-          });
+            for (int j = 0; j < kK; ++j) m[j] = o[j];
+            seg_ld26(sv(kVOg), cl, o); seg_st26(sv(kVOg), cl, g);
+#pragma unroll
+            for (int j = 0; j < kK; ++j) g[j] = o[j];
+            const float a = slp; slp = olp; olp = a;
+            s_is_right = dir;
+          }
+          if (__any_sync(0xffffffffu, sw)) cx.store_d(g);
+          seg_st26(sa.bx, cl, x);
+          seg_st26(sa.bg, cl, g);
         }
-        float blp = slp, ben = slp, bw = -INFINITY;
-        int n = 0;
-        bool c_prev = cont, nd = notdiv;
-        float esum_sub = 0.f;
-        const int nsteps = 1 << it;
-        const uint32_t* kud = ku + 2 * (nsteps - 1);
-#pragma unroll 1
-        for (int i = 0; i < nsteps; ++i, ++gt) {
-          if ((i & 3) == 0 && i + cx.slice < nsteps) {   // 4 leaves of multinomial uniforms, one per slice
-            Key kk{kud[2 * (i + cx.slice)], kud[2 * (i + cx.slice) + 1]};
-            lu[cx.slice][cx.cl] =
-                log1pf(-uniform_from_bits(bits_at(kk, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
-          }
-          // one leapfrog (leapfrog_integrator.py:280-309 with L = unrolled_leapfrog_steps)
-#pragma unroll
-          for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
-          bool stop = false;
-          float lu_i = 0.f;
-#pragma unroll 1
-          for (int l = 0; l < p.unrolled; ++l) {
-#pragma unroll
-            for (int j = 0; j < kK; ++j) x[j] = x[j] + eps * m[j];
-            cx.stage_a(x);
-            cx.contract();
-            if (l == 0) {
-              // read before the next barrier: a faster slice may overwrite lu[] for the next 4 leaves after it
-              lu_i = lu[i & 3][cx.cl];
-              // nuts.py:759 reduce_any(continue_tree): flag raised at the end of the previous leaf; leaving
-              // mid-leaf is harmless because no chain of the tile continues (ends/candidates are final)
-              if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
-              if (threadIdx.x == 0) sh.flags[(gt + 1) & 3] = 0;
-            }
-            if (stop) break;
-            cx.load_d(g);
-#pragma unroll
-            for (int j = 0; j < kK; ++j) m[j] = m[j] + eps * g[j];
-          }
-          if (stop) break;
-#pragma unroll
-          for (int j = 0; j < kK; ++j) m[j] = m[j] - heps * g[j];
-          n += c_prev ? 1 : 0;
-          // rho_subtree, checkpoint store / U-turn checks (nuts.py:826-869, 949-1010), chunk by chunk
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};   // <x - mu, g>, |m|^2, U-turn dots of the first check
-          const int pc = __popc(i);
-          const bool odd = (i & 1) != 0;
-          const int k0 = pc - (__ffs(~i) - 1);
-          float* ckm_w = sv(kVCk + pc);
-          float* ckr_w = sv(kVCk + p.max_depth + pc);
-          const float* ckm_r = sv(kVCk + k0);
-          const float* ckr_r = sv(kVCk + p.max_depth + k0);
-          for_chunks([&](auto off, auto nn) {
-            constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-            uint32_t rt[N];
-            tmem_ld<N>(rho_addr + OFF, rt);
-            tmem_wait_ld();
-            if (!odd) {
-#pragma unroll
-              for (int j = 0; j < N; ++j) {
-                ckm_w[(OFF + j) * kM] = m[OFF + j];
-                ckr_w[(OFF + j) * kM] = __uint_as_float(rt[j]);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-              const float rn = __uint_as_float(rt[j]) + m[OFF + j];
-              rt[j] = __float_as_uint(rn);
-              s4[0] = fmaf(x[OFF + j] - lc[OFF + j], g[OFF + j], s4[0]);
-              s4[1] = fmaf(m[OFF + j], m[OFF + j], s4[1]);
-            }
-            tmem_st<N>(rho_addr + OFF, rt);
-            if (odd) {
-#pragma unroll
-              for (int j = 0; j < N; ++j) {
-                const float diff = __uint_as_float(rt[j]) - ckr_r[(OFF + j) * kM];
-                s4[2] = fmaf(diff, ckm_r[(OFF + j) * kM], s4[2]);
-                s4[3] = fmaf(diff, m[OFF + j], s4[3]);
-              }
-            }
-          });
-          cx.reduce<4>(s4);
-          slp = fmaf(0.5f, s4[0], tp.lognorm);
-          bool ok = true;
-          if (odd) {
-            ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
-#pragma unroll 1
-            for (int k = k0 + 1; k < pc; ++k) {   // uniform trip count over the tile (lock-step leaf index)
-              const float* km = sv(kVCk + k);
-              const float* kr = sv(kVCk + p.max_depth + k);
-              float s2[2] = {0.f, 0.f};
-              for_chunks([&](auto off, auto nn) {
-                constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-                uint32_t rt[N];
-                tmem_ld<N>(rho_addr + OFF, rt);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                  const float diff = __uint_as_float(rt[j]) - kr[(OFF + j) * kM];
-                  s2[0] = fmaf(diff, km[(OFF + j) * kM], s2[0]);
-                  s2[1] = fmaf(diff, m[OFF + j], s2[1]);
-                }
-              });
-              cx.reduce<2>(s2);
-              ok = ok && (s2[0] >= 0.f) && (s2[1] >= 0.f);
-            }
-          }
-          float en = slp - 0.5f * s4[1];                 // nuts.py:871-877
-          en = isnan(en) ? -INFINITY : en;
-          const float dH = en - H0;
-          const bool nd_i = (-dH) < p.max_energy_diff;   // :880
-          const float w_new = log_add_exp(bw, dH);       // :881-883
-          const bool take = lu_i <= (dH - w_new);   // :897-901
-          if (take) {
-            float *bx = sv(kVBx), *bg = sv(kVBg);
-#pragma unroll
-            for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
-            blp = slp; ben = en;
-          }
-          bw = w_new;
-          const bool c_now = nd_i && c_prev;             // :921
-          if (c_now) esum_sub += expf(fminf(dH, 0.f));   // :930-933
-          nd = nd && (c_prev ? nd_i : true);             // :924-927,944
-          c_prev = ok && c_now;                          // :922
-          if (c_prev) sh.flags[gt & 3] = 1;
-        }
-        const bool cont_f = c_prev;
+        sa.eps = dir ? eps_abs : -eps_abs;
+        sa.nsteps = 1 << it;
+        sa.kud = ku + 2 * (sa.nsteps - 1);
+        SubtreeState st;
+        st.slp = slp; st.c_prev = cont; st.nd = notdiv;
+        nuts_subtree(cx, sh, lu, gt, sa, x, m, rho, st, pf);
+        slp = st.slp;
+        const bool cont_f = st.c_prev;
         // _loop_tree_doubling tail (nuts.py:597-711)
-        esum = esum_sub + esum;
-        const float tw = cont_f ? bw : -INFINITY;
+        esum = st.esum_sub + esum;
+        const float tw = cont_f ? st.bw : -INFINITY;
         const float wsum = log_add_exp(tw, cw);
         float thr = tw - cw;
         thr = isnan(thr) ? 0.f : thr;
         const bool swap = (lacc <= thr) && cont_f;
         cw = wsum;
         if (swap) {
-          float *bx = sv(kVBx), *bg = sv(kVBg), *ccx = sv(kVCx), *ccg = sv(kVCg);
-#pragma unroll
-          for (int j = 0; j < kK; ++j) { ccx[j * kM] = bx[j * kM]; ccg[j * kM] = bg[j * kM]; }
-          clp = blp; cen = ben;
+          float o[kK];
+          seg_ld26(sa.bx, cl, o); seg_st26(sv(kVCx), cl, o);
+          seg_ld26(sa.bg, cl, o); seg_st26(sv(kVCg), cl, o);
+          clp = st.blp; cen = st.ben;
         }
         float s2[2] = {0.f, 0.f};
         {
-          float* rh = sv(kVRho);
-          const float* om = sv(kVOm);
-          for_chunks([&](auto off, auto nn) {
-            constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-            uint32_t rt[N];
-            tmem_ld<N>(rho_addr + OFF, rt);
-            tmem_wait_ld();
+          float rh[kK], om[kK];
+          seg_ld26(sv(kVRho), cl, rh);
+          seg_ld26(sv(kVOm), cl, om);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-              const float rr = rh[(OFF + j) * kM] + __uint_as_float(rt[j]);
-              rh[(OFF + j) * kM] = rr;
-              s2[0] = fmaf(rr, m[OFF + j], s2[0]);
-              s2[1] = fmaf(rr, om[(OFF + j) * kM], s2[1]);
-            }
-          });
+          for (int j = 0; j < kK; ++j) {
+            const float rr = rh[j] + rho[j];
+            rh[j] = rr;
+            s2[0] = fmaf(rr, m[j], s2[0]);
+            s2[1] = fmaf(rr, om[j], s2[1]);
+          }
+          seg_st26(sv(kVRho), cl, rh);
         }
         cx.reduce<2>(s2);
-        nleap += n;
+        nleap += st.n;
         accepted = accepted || swap;
-        notdiv = nd;
+        notdiv = st.nd;
         cont = cont_f && (s2[0] >= 0.f) && (s2[1] >= 0.f);
         any_cont = __syncthreads_or(cont ? 1 : 0);       // nuts.py:404-407
       }
       // ---- results (nuts.py:424-445); the next state is the trajectory candidate
-      {
-        const float *ccx = sv(kVCx), *ccg = sv(kVCg);
-#pragma unroll
-        for (int j = 0; j < kK; ++j) { x[j] = ccx[j * kM]; g[j] = ccg[j * kM]; }
-      }
+      float g[kK];
+      seg_ld26(sv(kVCx), cl, x);
+      seg_ld26(sv(kVCg), cl, g);
+      cx.store_d(g);
       lp = clp;
       const int leap = nleap * p.unrolled;
       nleap_total += (unsigned long long)leap;
@@ -443,8 +331,12 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         }
       }
     }
-    tile_store(p.x, 0, p.B, c, D, cx.slice, live, x);
-    tile_store(p.g, 0, p.B, c, D, cx.slice, live, g);
+    {
+      float g[kK];
+      cx.load_d(g);
+      tile_store(p.x, 0, p.B, c, D, cx.slice, live, x);
+      tile_store(p.g, 0, p.B, c, D, cx.slice, live, g);
+    }
     if (live && cx.slice == 0) {
       p.lp[c] = lp;
       if (p.leapfrog_total) p.leapfrog_total[c] += nleap_total;
@@ -466,9 +358,27 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
   return p.B >= 2 * kM;
 }
 
+#ifdef PB2_TILE_PROF
+static void dump_tile_prof(pb2_ctx* ctx) {
+  unsigned long long h[2][16];
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpyFromSymbol(h, tile::g_tile_prof, sizeof(h));
+  static const char* nm[7] = {"head", "kick+stage", "contract", "post", "reduce4", "extra checks", "scalars+take"};
+  for (int w = 0; w < 2; ++w) {
+    fprintf(stderr, "[tileprof t%d] leaves %llu:", w ? 511 : 0, h[w][15]);
+    for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.0f", nm[k], h[w][15] ? (double)h[w][k] / h[w][15] : 0.0);
+    fprintf(stderr, "\n");
+  }
+  unsigned long long z[2][16] = {};
+  cudaMemcpyToSymbol(tile::g_tile_prof, z, sizeof(z));
+}
+#else
+static void dump_tile_prof(pb2_ctx*) {}
+#endif
+
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p) {
   DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, tgt->dim};
-  const size_t smem = 2 * (size_t)kPlaneBytes;
+  size_t smem = 2 * (size_t)kPlaneBytes;
   const int ntiles = (p.B + kM - 1) / kM;
   const int grid = std::min(ntiles, ctx->num_sms);
   if (mode == kModeHMC) {
@@ -479,6 +389,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "tile_hmc_kernel");
   }
+  smem += 2 * kVS * sizeof(float);   // NUTS: + the previous leaf's checkpoint (momentum, rho)
   // fused multi-transition NUTS runs: chains re-grouped at doubling boundaries (pb2_tile_sched.cuh)
   const int kS0 = 5;
   if (mode == kModeNUTS && ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 &&
@@ -516,6 +427,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
       return rc;
     tile_nuts_sched_kernel<<<sgrid, kThreads, smem, ctx->stream>>>(p, tp, sp, ctx->d_ckpt);
     ctx->launches += 2;
+    dump_tile_prof(ctx);
     if (sp.stats) {
       unsigned long long h[32];
       cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
@@ -523,7 +435,8 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
       fprintf(stderr, "[sched] tasks %llu chains %llu (fill %.1f) ticks %llu idle-polls %llu | per class tasks:", h[0], h[1],
               h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3]);
       for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu(%.0f)", h[8 + k], h[8 + k] ? (double)h[20 + k] / h[8 + k] : 0.0);
-      fprintf(stderr, "\n");
+      fprintf(stderr, "\n[sched] Mcycles summed over CTAs: claim %.1f idle %.1f load %.1f run %.1f publish %.1f (run = %.0f cycles per tile leaf)\n",
+              h[26] * 1e-6, h[27] * 1e-6, h[28] * 1e-6, h[29] * 1e-6, h[30] * 1e-6, h[2] ? (double)h[29] / h[2] : 0.0);
     }
     return check_cuda(ctx, cudaGetLastError(), "tile_nuts_sched_kernel");
   }
@@ -542,6 +455,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
       return rc;
     tile_nuts_kernel<<<grid, kThreads, smem, ctx->stream>>>(p, tp, ctx->d_ckpt);
     ctx->launches += 1;
+    dump_tile_prof(ctx);
     return check_cuda(ctx, cudaGetLastError(), "tile_nuts_kernel");
   }
   return set_error(ctx, PB2_ERR_UNSUPPORTED, "tile path: unsupported mode");

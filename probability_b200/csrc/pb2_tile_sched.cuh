@@ -15,7 +15,7 @@
 // candidate, rho and the scalars); the subtree candidate and the checkpoint stores are dead at a
 // boundary and stay in the CTA's scratch.
 #pragma once
-#include "pb2_tile.cuh"
+#include "pb2_tile_nuts.cuh"
 
 namespace pb2 {
 using namespace tile;
@@ -52,21 +52,35 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
   __shared__ int n_claimed, n_done, sel_cls;
   Ctx cx;
   cx.init(&sh, planes, tp.P, tp.loc, tp.D);
+  Prof pf;
+  pf.init();
   const int D = tp.D;
   const int tid = threadIdx.x;
-  constexpr size_t kVS = (size_t)kKP * kM;
-  // CTA scratch: subtree candidate (x, g) + checkpoint stores, [vector][dim][lane]
+  const int cl = cx.cl;
+  // CTA scratch: subtree candidate (x, g) + checkpoint stores; per-thread segments (pb2_tile.cuh seg_*)
   enum { kTBx = 0, kTBg = 1, kTCk = 2 };
   const int nvec = kTCk + 2 * p.max_depth;
-  float* const scr_t = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM + cx.cl;
-  auto sv = [&](int v) -> float* { return scr_t + (size_t)v * kVS; };
-  const float* lc = sh.loc + kK * cx.slice;
-  const uint32_t rho_addr = cx.lane_addr + kColRho + kK * cx.slice;
+  float* const scr_s = scratch_all + (size_t)blockIdx.x * nvec * kVS + (size_t)(kK * cx.slice) * kM;
+  SubtreeArgs sa;
+  sa.unrolled = p.unrolled; sa.layout = p.layout; sa.b_global = (uint64_t)p.B_global;
+  sa.lognorm = tp.lognorm; sa.max_energy_diff = p.max_energy_diff;
+  sa.lc = sh.loc + kK * cx.slice;
+  sa.bx = scr_s + (size_t)kTBx * kVS; sa.bg = scr_s + (size_t)kTBg * kVS; sa.ck = scr_s + (size_t)kTCk * kVS;
+  sa.max_depth = p.max_depth;
+  sa.ckl = reinterpret_cast<float*>(planes + 2 * kPlaneBytes) + (size_t)(kK * cx.slice) * kM;
   const int nclass = 1 + max(0, p.max_depth - sp.s0);
   unsigned gt = 0;
   int patience = 0;                 // consecutive polls without a full tile (uniform across the CTA)
   const int scan0 = (int)(((long long)blockIdx.x * p.B) / gridDim.x);   // de-correlate the CTAs' scans
 
+  long long tmark = clock64();
+  auto lap = [&](int k) {   // thread 0 of every CTA: cycles per scheduler phase (only with PB2_SCHED_STATS)
+    if (sp.stats && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(sp.stats + k, (unsigned long long)(now - tmark));
+      tmark = now;
+    }
+  };
   while (true) {
     // ------------------------------------------------------------ (1) what is ready?
     __syncthreads();   // everybody is done reading the shared scheduling words of the previous round
@@ -107,6 +121,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
       if (sp.stats && tid == 0) atomicAdd(sp.stats + 3, 1ull);
       patience++;
       __nanosleep(10000);
+      lap(27);
       continue;
     }
     // ------------------------------------------------------------ (2) claim up to 128 chains of that class
@@ -122,7 +137,8 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     }
     __syncthreads();
     const int ntask = min(n_claimed, kM);
-    if (ntask == 0) continue;
+    if (ntask == 0) { lap(27); continue; }
+    lap(26);
     patience = 0;
     if (sp.stats && tid == 0) {
       atomicAdd(sp.stats + 0, 1ull);
@@ -143,19 +159,22 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     const uint32_t* sk = p.sched + (size_t)(t - p.t_sched0) * p.sched_stride;
     const uint32_t* hdr = sk + 2 * p.n_parts;
     const uint32_t* ku = hdr + 6 * p.max_depth;
-    float x[kK], m[kK], g[kK];
+    sa.cg = cg;
+    float x[kK], m[kK], rho[kK];
     float lp, H0, slp, olp, clp, cen, cw, esum;
     int nleap;
     bool cont, notdiv, accepted, s_is_right;
     int it_begin, it_end;
     if (cls == 0) {
       // ---- _start_trajectory_batched (nuts.py:512-539)
+      float g[kK];
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
         const bool in = live && (kK * cx.slice + j < D);
         x[j] = in ? __ldcg(p.x + (size_t)c * D + kK * cx.slice + j) : 0.f;
         g[j] = in ? __ldcg(p.g + (size_t)c * D + kK * cx.slice + j) : 0.f;
       }
+      cx.store_d(g);
       lp = live ? __ldcg(p.lp + c) : 0.f;
       float s1[1] = {0.f};
 #pragma unroll
@@ -178,12 +197,14 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
       it_begin = 0;
       it_end = min(sp.s0, p.max_depth);
     } else {
+      float g[kK];
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
         x[j] = live ? __ldcg(&rec[kRSx * kKP + j]) : 0.f;
         m[j] = live ? __ldcg(&rec[kRSm * kKP + j]) : 0.f;
         g[j] = live ? __ldcg(&rec[kRSg * kKP + j]) : 0.f;
       }
+      cx.store_d(g);
       lp = live ? __ldcg(&rs[kSLp]) : 0.f;  H0 = live ? __ldcg(&rs[kSH0]) : 0.f;  slp = live ? __ldcg(&rs[kSSlp]) : 0.f;
       olp = live ? __ldcg(&rs[kSOlp]) : 0.f;  clp = live ? __ldcg(&rs[kSClp]) : 0.f;  cen = live ? __ldcg(&rs[kSCen]) : 0.f;
       cw = live ? __ldcg(&rs[kSCw]) : 0.f;  esum = live ? __ldcg(&rs[kSEsum]) : 0.f;
@@ -193,197 +214,82 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
       it_begin = sp.s0 + cls - 1;
       it_end = it_begin + 1;
     }
+    sa.H0 = H0;
     int any_cont = __syncthreads_or(cont ? 1 : 0);
+    lap(28);
 #pragma unroll 1
     for (int it = it_begin; it < it_end && any_cont; ++it) {
       Key kd{hdr[6 * it], hdr[6 * it + 1]}, kac{hdr[6 * it + 2], hdr[6 * it + 3]};
       const bool dir = (bits_at(kd, cg, (uint64_t)p.B_global, p.layout) & 1u) != 0;
       const float lacc = log1pf(-uniform_from_bits(bits_at(kac, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
-      if (live && dir != s_is_right) {
-#pragma unroll
-        for (int j = 0; j < kK; ++j) {
-          float a;
-          a = __ldcg(&rec[kROx * kKP + j]); rec[kROx * kKP + j] = x[j]; x[j] = a;
-          a = __ldcg(&rec[kROm * kKP + j]); rec[kROm * kKP + j] = m[j]; m[j] = a;
-          a = __ldcg(&rec[kROg * kKP + j]); rec[kROg * kKP + j] = g[j]; g[j] = a;
-        }
-        const float a = slp; slp = olp; olp = a;
-        s_is_right = dir;
-      }
-      const float eps = dir ? eps_abs : -eps_abs;
-      const float heps = 0.5f * eps;
       {
-        float *bx = sv(kTBx), *bg = sv(kTBg);
+        const bool sw = live && dir != s_is_right;
+        float g[kK];
+        cx.load_d(g);
+        if (sw) {
 #pragma unroll
-        for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
-        for_chunks([&](auto off, auto n) {
-          constexpr int OFF = decltype(off)::value, N = decltype(n)::value;
-          uint32_t z[N];
-#pragma unroll
-          for (int j = 0; j < N; ++j) z[j] = 0u;
-          tmem_st<N>(rho_addr + OFF, z);
-        });
+          for (int j = 0; j < kK; ++j) {
+            float a;
+            a = __ldcg(&rec[kROx * kKP + j]); rec[kROx * kKP + j] = x[j]; x[j] = a;
+            a = __ldcg(&rec[kROm * kKP + j]); rec[kROm * kKP + j] = m[j]; m[j] = a;
+            a = __ldcg(&rec[kROg * kKP + j]); rec[kROg * kKP + j] = g[j]; g[j] = a;
+          }
+          const float a = slp; slp = olp; olp = a;
+          s_is_right = dir;
+        }
+        if (__any_sync(0xffffffffu, sw)) cx.store_d(g);
+        seg_st26(sa.bx, cl, x);
+        seg_st26(sa.bg, cl, g);
       }
-      float blp = slp, ben = slp, bw = -INFINITY;
-      int n = 0;
-      bool c_prev = cont, nd = notdiv;
-      float esum_sub = 0.f;
-      const int nsteps = 1 << it;
-      const uint32_t* kud = ku + 2 * (nsteps - 1);
-#pragma unroll 1
-      for (int i = 0; i < nsteps; ++i, ++gt) {
-        if ((i & 3) == 0 && i + cx.slice < nsteps) {
-          Key kk{kud[2 * (i + cx.slice)], kud[2 * (i + cx.slice) + 1]};
-          lu[cx.slice][cx.cl] = log1pf(-uniform_from_bits(bits_at(kk, cg, (uint64_t)p.B_global, p.layout), 0.f, 1.f));
-        }
-#pragma unroll
-        for (int j = 0; j < kK; ++j) m[j] = m[j] + heps * g[j];
-        bool stop = false;
-        float lu_i = 0.f;
-#pragma unroll 1
-        for (int l = 0; l < p.unrolled; ++l) {
-#pragma unroll
-          for (int j = 0; j < kK; ++j) x[j] = x[j] + eps * m[j];
-          cx.stage_a(x);
-          cx.contract();
-          if (l == 0) {
-            // read before the next barrier: a faster slice may overwrite lu[] for the next 4 leaves after it
-            lu_i = lu[i & 3][cx.cl];
-            if (i > 0 && sh.flags[(gt - 1) & 3] == 0) stop = true;
-            if (tid == 0) sh.flags[(gt + 1) & 3] = 0;
-          }
-          if (stop) break;
-          cx.load_d(g);
-#pragma unroll
-          for (int j = 0; j < kK; ++j) m[j] = m[j] + eps * g[j];
-        }
-        if (stop) break;
-#pragma unroll
-        for (int j = 0; j < kK; ++j) m[j] = m[j] - heps * g[j];
-        n += c_prev ? 1 : 0;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        const int pc = __popc(i);
-        const bool odd = (i & 1) != 0;
-        const int k0 = pc - (__ffs(~i) - 1);
-        float* ckm_w = sv(kTCk + pc);
-        float* ckr_w = sv(kTCk + p.max_depth + pc);
-        const float* ckm_r = sv(kTCk + k0);
-        const float* ckr_r = sv(kTCk + p.max_depth + k0);
-        for_chunks([&](auto off, auto nn) {
-          constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-          uint32_t rt[N];
-          tmem_ld<N>(rho_addr + OFF, rt);
-          tmem_wait_ld();
-          if (!odd) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-              ckm_w[(OFF + j) * kM] = m[OFF + j];
-              ckr_w[(OFF + j) * kM] = __uint_as_float(rt[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < N; ++j) {
-            const float rn = __uint_as_float(rt[j]) + m[OFF + j];
-            rt[j] = __float_as_uint(rn);
-            s4[0] = fmaf(x[OFF + j] - lc[OFF + j], g[OFF + j], s4[0]);
-            s4[1] = fmaf(m[OFF + j], m[OFF + j], s4[1]);
-          }
-          tmem_st<N>(rho_addr + OFF, rt);
-          if (odd) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-              const float diff = __uint_as_float(rt[j]) - ckr_r[(OFF + j) * kM];
-              s4[2] = fmaf(diff, ckm_r[(OFF + j) * kM], s4[2]);
-              s4[3] = fmaf(diff, m[OFF + j], s4[3]);
-            }
-          }
-        });
-        cx.reduce<4>(s4);
-        slp = fmaf(0.5f, s4[0], tp.lognorm);
-        bool ok = true;
-        if (odd) {
-          ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
-#pragma unroll 1
-          for (int k = k0 + 1; k < pc; ++k) {
-            const float* km = sv(kTCk + k);
-            const float* kr = sv(kTCk + p.max_depth + k);
-            float s2[2] = {0.f, 0.f};
-            for_chunks([&](auto off, auto nn) {
-              constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-              uint32_t rt[N];
-              tmem_ld<N>(rho_addr + OFF, rt);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < N; ++j) {
-                const float diff = __uint_as_float(rt[j]) - kr[(OFF + j) * kM];
-                s2[0] = fmaf(diff, km[(OFF + j) * kM], s2[0]);
-                s2[1] = fmaf(diff, m[OFF + j], s2[1]);
-              }
-            });
-            cx.reduce<2>(s2);
-            ok = ok && (s2[0] >= 0.f) && (s2[1] >= 0.f);
-          }
-        }
-        float en = slp - 0.5f * s4[1];
-        en = isnan(en) ? -INFINITY : en;
-        const float dH = en - H0;
-        const bool nd_i = (-dH) < p.max_energy_diff;
-        const float w_new = log_add_exp(bw, dH);
-        const bool take = lu_i <= (dH - w_new);
-        if (take) {
-          float *bx = sv(kTBx), *bg = sv(kTBg);
-#pragma unroll
-          for (int j = 0; j < kK; ++j) { bx[j * kM] = x[j]; bg[j * kM] = g[j]; }
-          blp = slp; ben = en;
-        }
-        bw = w_new;
-        const bool c_now = nd_i && c_prev;
-        if (c_now) esum_sub += expf(fminf(dH, 0.f));
-        nd = nd && (c_prev ? nd_i : true);
-        c_prev = ok && c_now;
-        if (c_prev) sh.flags[gt & 3] = 1;
-      }
-      const bool cont_f = c_prev;
-      esum = esum_sub + esum;
-      const float tw = cont_f ? bw : -INFINITY;
+      sa.eps = dir ? eps_abs : -eps_abs;
+      sa.nsteps = 1 << it;
+      sa.kud = ku + 2 * (sa.nsteps - 1);
+      SubtreeState st;
+      st.slp = slp; st.c_prev = cont; st.nd = notdiv;
+      nuts_subtree(cx, sh, lu, gt, sa, x, m, rho, st, pf);
+      slp = st.slp;
+      const bool cont_f = st.c_prev;
+      esum = st.esum_sub + esum;
+      const float tw = cont_f ? st.bw : -INFINITY;
       const float wsum = log_add_exp(tw, cw);
       float thr = tw - cw;
       thr = isnan(thr) ? 0.f : thr;
       const bool swap = (lacc <= thr) && cont_f;
       cw = wsum;
       if (swap && live) {
-        const float *bx = sv(kTBx), *bg = sv(kTBg);
+        float o[kK];
+        seg_ld26(sa.bx, cl, o);
 #pragma unroll
-        for (int j = 0; j < kK; ++j) { rec[kRCx * kKP + j] = bx[j * kM]; rec[kRCg * kKP + j] = bg[j * kM]; }
-        clp = blp; cen = ben;
+        for (int j = 0; j < kK; ++j) rec[kRCx * kKP + j] = o[j];
+        seg_ld26(sa.bg, cl, o);
+#pragma unroll
+        for (int j = 0; j < kK; ++j) rec[kRCg * kKP + j] = o[j];
+        clp = st.blp; cen = st.ben;
       }
       float s2[2] = {0.f, 0.f};
-      for_chunks([&](auto off, auto nn) {
-        constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
-        uint32_t rt[N];
-        tmem_ld<N>(rho_addr + OFF, rt);
-        tmem_wait_ld();
-        if (live) {
+      if (live) {
 #pragma unroll
-          for (int j = 0; j < N; ++j) {
-            const float rr = __ldcg(&rec[kRRho * kKP + OFF + j]) + __uint_as_float(rt[j]);
-            rec[kRRho * kKP + OFF + j] = rr;
-            s2[0] = fmaf(rr, m[OFF + j], s2[0]);
-            s2[1] = fmaf(rr, __ldcg(&rec[kROm * kKP + OFF + j]), s2[1]);
-          }
+        for (int j = 0; j < kK; ++j) {
+          const float rr = __ldcg(&rec[kRRho * kKP + j]) + rho[j];
+          rec[kRRho * kKP + j] = rr;
+          s2[0] = fmaf(rr, m[j], s2[0]);
+          s2[1] = fmaf(rr, __ldcg(&rec[kROm * kKP + j]), s2[1]);
         }
-      });
+      }
       cx.reduce<2>(s2);
-      nleap += n;
+      nleap += st.n;
       accepted = accepted || swap;
-      notdiv = nd;
+      notdiv = st.nd;
       cont = cont_f && (s2[0] >= 0.f) && (s2[1] >= 0.f);
       any_cont = __syncthreads_or(cont ? 1 : 0);
     }
     if (sp.stats && tid == 0) atomicAdd(sp.stats + 2, (unsigned long long)(gt - gt_begin));
+    lap(29);
     // ------------------------------------------------------------ (4) publish: finished transition or next doubling
     const bool finished = !cont || it_end >= p.max_depth;
     int next_ready = kReadyRunning;
+    float gend[kK];
+    cx.load_d(gend);   // gradient at the moving end (warp-aligned TMEM read, before the per-chain branches)
     if (live) {
       if (finished) {
         float fx[kK], fg[kK];
@@ -420,7 +326,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
       } else {
 #pragma unroll
         for (int j = 0; j < kK; ++j) {
-          rec[kRSx * kKP + j] = x[j]; rec[kRSm * kKP + j] = m[j]; rec[kRSg * kKP + j] = g[j];
+          rec[kRSx * kKP + j] = x[j]; rec[kRSm * kKP + j] = m[j]; rec[kRSg * kKP + j] = gend[j];
         }
         if (cx.slice == 0) {
           rs[kSLp] = lp; rs[kSH0] = H0; rs[kSSlp] = slp; rs[kSOlp] = olp; rs[kSClp] = clp; rs[kSCen] = cen;
@@ -434,6 +340,7 @@ tile_nuts_sched_kernel(const ChainParams p, const DenseGaussianParams tp, const 
     __threadfence();
     __syncthreads();   // all four slices of every chain have written their part of the record
     if (live && cx.slice == 0) atomicExch(sp.ready + c, next_ready);
+    lap(30);
   }
   cx.finish();
 }
