@@ -183,7 +183,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   sa.unrolled = p.unrolled; sa.layout = p.layout; sa.b_global = (uint64_t)p.B_global;
   sa.lognorm = tp.lognorm; sa.max_energy_diff = p.max_energy_diff;
   sa.lc = sh.loc + kK * cx.slice;
-  sa.bx = sv(kVBx); sa.bg = sv(kVBg); sa.ck = sv(kVCk); sa.max_depth = p.max_depth;
+  sa.bx = sv(kVBx); sa.bg = sv(kVBg); sa.ck_m = sv(kVCk); sa.ck_r = sv(kVCk + p.max_depth);
   sa.ckl = reinterpret_cast<float*>(planes + 2 * kPlaneBytes) + (size_t)(kK * cx.slice) * kM;
   const int ntiles = (p.B + kM - 1) / kM;
   unsigned gt = 0;   // global leaf counter (rotates the "somebody continues" flags)
@@ -266,7 +266,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
         sa.kud = ku + 2 * (sa.nsteps - 1);
         SubtreeState st;
         st.slp = slp; st.c_prev = cont; st.nd = notdiv;
-        nuts_subtree(cx, sh, lu, gt, sa, x, m, rho, st, pf);
+        nuts_subtree<false>(cx, sh, lu, gt, sa, x, m, rho, st, pf);
         slp = st.slp;
         const bool cont_f = st.c_prev;
         // _loop_tree_doubling tail (nuts.py:597-711)
@@ -390,15 +390,18 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     return check_cuda(ctx, cudaGetLastError(), "tile_hmc_kernel");
   }
   smem += 2 * kVS * sizeof(float);   // NUTS: + the previous leaf's checkpoint (momentum, rho)
-  // fused multi-transition NUTS runs: chains re-grouped at doubling boundaries (pb2_tile_sched.cuh)
-  const int kS0 = 5;
+  // fused multi-transition NUTS runs: chains re-grouped every 32 leaves (pb2_tile_sched.cuh)
   if (mode == kModeNUTS && ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 &&
       p.max_depth > kS0) {
     const int sgrid = getenv("PB2_SCHED_GRID") ? atoi(getenv("PB2_SCHED_GRID")) : ctx->num_sms;
-    const size_t scr_bytes = (size_t)sgrid * (2 + 2 * p.max_depth) * kKP * kM * sizeof(float);
-    const size_t vec_bytes = (size_t)p.B * kRecVecs * kKP * sizeof(float);
-    const size_t scal_bytes = (size_t)p.B * kRecScal * sizeof(float);
-    const size_t need = scr_bytes + vec_bytes + scal_bytes + (size_t)p.B * sizeof(int);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    SchedParams sp;
+    sp.nrv = kRHi + 2 * (p.max_depth - kS0);
+    const size_t scr_bytes = up((size_t)sgrid * (2 + 2 * kS0) * kVS * sizeof(float));
+    const size_t vec_bytes = up((size_t)p.B * sp.nrv * kRecStride * sizeof(float));
+    const size_t scal_bytes = up((size_t)p.B * kRecScal * sizeof(float));
+    const size_t queue_bytes = up((size_t)2 * p.B * sizeof(int));
+    const size_t need = scr_bytes + vec_bytes + scal_bytes + queue_bytes + kQWords * sizeof(unsigned long long);
     if (need > ctx->ckpt_bytes) {
       if (ctx->d_ckpt) cudaFree(ctx->d_ckpt);
       ctx->d_ckpt = nullptr;
@@ -407,12 +410,11 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
       ctx->ckpt_bytes = need;
     }
     unsigned char* base = reinterpret_cast<unsigned char*>(ctx->d_ckpt);
-    SchedParams sp;
     sp.rec_vec = reinterpret_cast<float*>(base + scr_bytes);
     sp.rec_scal = reinterpret_cast<float*>(base + scr_bytes + vec_bytes);
-    sp.ready = reinterpret_cast<int*>(base + scr_bytes + vec_bytes + scal_bytes);
-    sp.s0 = kS0;
-    sp.patience = getenv("PB2_SCHED_PATIENCE") ? atoi(getenv("PB2_SCHED_PATIENCE")) : 24;
+    sp.queue = reinterpret_cast<int*>(base + scr_bytes + vec_bytes + scal_bytes);
+    sp.qctl = reinterpret_cast<unsigned long long*>(base + scr_bytes + vec_bytes + scal_bytes + queue_bytes);
+    sp.patience = getenv("PB2_SCHED_PATIENCE") ? atoi(getenv("PB2_SCHED_PATIENCE")) : 50;
     sp.stats = nullptr;
     static unsigned long long* d_stats = nullptr;
     if (getenv("PB2_SCHED_STATS")) {
@@ -420,7 +422,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
       cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), ctx->stream);
       sp.stats = d_stats;
     }
-    tile_sched_init_kernel<<<(p.B + 255) / 256, 256, 0, ctx->stream>>>(sp.ready, sp.rec_scal, p.B, p.t0);
+    tile_sched_init_kernel<<<(p.B + 255) / 256, 256, 0, ctx->stream>>>(sp, p.B, p.t0);
     if (int rc = check_cuda(ctx, cudaFuncSetAttribute(tile_nuts_sched_kernel,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(tile_nuts_sched)"))

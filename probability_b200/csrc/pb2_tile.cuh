@@ -222,10 +222,11 @@ struct Ctx {
       uint32_t hi[N], lo[N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
+        // round-to-nearest tf32 split with integer ops (cvt.rna.tf32.f32 is emulated with ~5 instructions on
+        // sm_100a: inf/nan handling this path does not need -- a non-finite x gives a NaN energy = divergence)
         const float v = x[OFF + j] - lc[OFF + j];
-        const float h = tf32_rna(v);
-        hi[j] = __float_as_uint(h);
-        lo[j] = __float_as_uint(tf32_rna(v - h));
+        hi[j] = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+        lo[j] = (__float_as_uint(v - __uint_as_float(hi[j])) + 0x1000u) & 0xffffe000u;
       }
       tmem_st<N>(base + kColAhi + OFF, hi);
       tmem_st<N>(base + kColAlo + OFF, lo);

@@ -49,6 +49,7 @@ struct SubtreeState {
   int n;            // leaves this chain took
   bool c_prev;      // in: chain continues; out: subtree finished without U-turn / divergence
   bool nd;          // not diverged
+  bool took;        // out: a new subtree candidate was written to the scratch (bx, bg) during this call
 };
 
 struct SubtreeArgs {
@@ -61,10 +62,53 @@ struct SubtreeArgs {
   const float* lc;       // loc of my slice (shared memory)
   float* bx;             // L2 scratch, slice bases: subtree candidate (x, g)
   float* bg;
-  float* ck;             // checkpoint stores: momentum of slot k at ck + k * kVS, rho at ck + (max_depth + k) * kVS
-  int max_depth;
+  float* ck_m;           // checkpoint stores: momentum of slot k at ck_m + k * kVS, rho at ck_r + k * kVS
+  float* ck_r;
   float* ckl;            // shared memory, slice base: last even leaf's checkpoint (momentum; rho at + kVS)
+  // kMixed only (32-leaf chunks of doublings >= 5, every chain at its own chunk of its own doubling):
+  float* hck;            // this chain's record: checkpoints of chunk-first leaves, slot s = (m at 2s, rho at 2s + 1) * kRecStride
+  int ihi;               // my chunk index within my doubling
+  int hi_slot_w;         // >= 0: leaf 0 of this chunk is checked again by later chunks -> store it in slot hi_slot_w
+  int hi_checks;         // tile-wide max of trailing_ones(ihi): number of cross-chunk U-turn checks at the last leaf
 };
+
+// ---- chain-major records (pb2_tile_sched.cuh): a vector is 4 slices x 28 floats (26 used; 16-byte aligned segments)
+constexpr int kRecSlice = 28, kRecStride = 4 * kRecSlice;
+template <int OFF, int N>
+__device__ __forceinline__ void rec_ld(const float* vb, float (&v)[N]) {
+  if constexpr (N == 2) {
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(vb + OFF));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(vb + OFF + 4 * q));
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  }
+}
+template <int OFF, int N>
+__device__ __forceinline__ void rec_st(float* vb, const float* v) {
+  if constexpr (N == 2) {
+    __stcg(reinterpret_cast<float2*>(vb + OFF), make_float2(v[0], v[1]));
+  } else {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      __stcg(reinterpret_cast<float4*>(vb + OFF + 4 * q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
+}
+__device__ __forceinline__ void rec_ld26(const float* vb, float (&v)[kK]) {
+  float a[16], b[8], c[2];
+  rec_ld<0, 16>(vb, a); rec_ld<16, 8>(vb, b); rec_ld<24, 2>(vb, c);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = a[j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[16 + j] = b[j];
+  v[24] = c[0]; v[25] = c[1];
+}
+__device__ __forceinline__ void rec_st26(float* vb, const float (&v)[kK]) {
+  rec_st<0, 16>(vb, v); rec_st<16, 8>(vb, v + 16); rec_st<24, 2>(vb, v + 24);
+}
 
 constexpr size_t kVS = (size_t)kKP * kM;   // floats per scratch vector
 
@@ -105,15 +149,20 @@ __device__ __forceinline__ void uturn_pair(const float* km0, const float* kr0, c
 // On entry: x, m = the end that is extended, g(x) in TMEM D.  On exit the same for the new end, rho = sum of the
 // subtree's momenta, st = the subtree's scalars.  `gt` counts leaves globally (it rotates the flags through which
 // the tile learns that no chain continues, nuts.py:759 reduce_any(continue_tree)).
+template <bool kMixed>
 __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM], unsigned& gt, const SubtreeArgs& a,
                                              float (&x)[kK], float (&m)[kK], float (&rho)[kK], SubtreeState& st, Prof& pf) {
   const float eps = a.eps, heps = 0.5f * a.eps;
   const int cl = cx.cl;
   float slp = st.slp, blp = st.slp, ben = st.slp, bw = -INFINITY, esum_sub = 0.f;
   int n = 0;
-  bool c_prev = st.c_prev, nd = st.nd;
+  bool c_prev = st.c_prev, nd = st.nd, took = false;
+  if constexpr (kMixed) {   // a chunk continues a subtree: the caller loaded (or initialised) rho and the scalars
+    blp = st.blp; ben = st.ben; bw = st.bw; esum_sub = st.esum_sub; n = st.n;
+  } else {
 #pragma unroll
-  for (int j = 0; j < kK; ++j) rho[j] = 0.f;
+    for (int j = 0; j < kK; ++j) rho[j] = 0.f;
+  }
 #pragma unroll 1
   for (int i = 0; i < a.nsteps; ++i, ++gt) {
     pf.mark(0);
@@ -166,8 +215,8 @@ __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM
     const bool odd = (i & 1) != 0;
     const int ones = __ffs(~i) - 1;          // trailing ones: the leaf closes subtrees of 2, 4, .., 2^ones leaves
     const bool keep = (i & 3) == 0;          // an even leaf that is checked again after leaf i + 1
-    float* const ckm_w = a.ck + (size_t)pc * kVS;
-    float* const ckr_w = a.ck + (size_t)(a.max_depth + pc) * kVS;
+    float* const ckm_w = a.ck_m + (size_t)pc * kVS;
+    float* const ckr_w = a.ck_r + (size_t)pc * kVS;
     for_chunks([&](auto off, auto nn) {
       constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
       float gc[N];
@@ -185,6 +234,12 @@ __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM
         if (keep) {
           seg_st<OFF, N>(ckm_w, cl, m + OFF);
           seg_st<OFF, N>(ckr_w, cl, rho + OFF);
+        }
+        if constexpr (kMixed) {
+          if (i == 0 && a.hi_slot_w >= 0) {
+            rec_st<OFF, N>(a.hck + (size_t)(2 * a.hi_slot_w) * kRecStride, m + OFF);
+            rec_st<OFF, N>(a.hck + (size_t)(2 * a.hi_slot_w + 1) * kRecStride, rho + OFF);
+          }
         }
       }
 #pragma unroll
@@ -214,10 +269,41 @@ __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM
         const bool two = k + 1 < pc - 1;
         const int k1 = two ? k + 1 : k;
         float s[4] = {0.f, 0.f, 0.f, 0.f};
-        uturn_pair(a.ck + (size_t)k * kVS, a.ck + (size_t)(a.max_depth + k) * kVS, a.ck + (size_t)k1 * kVS,
-                   a.ck + (size_t)(a.max_depth + k1) * kVS, cl, rho, m, s);
+        uturn_pair(a.ck_m + (size_t)k * kVS, a.ck_r + (size_t)k * kVS, a.ck_m + (size_t)k1 * kVS,
+                   a.ck_r + (size_t)k1 * kVS, cl, rho, m, s);
         cx.reduce<4>(s);
         ok = ok && (s[0] >= 0.f) && (s[1] >= 0.f) && (s[2] >= 0.f) && (s[3] >= 0.f);
+      }
+      if constexpr (kMixed) {
+        // last leaf of the chunk: the subtrees of 64, 128, .. leaves it closes start at the first leaf of an
+        // earlier chunk of this chain's doubling (per-chain slots in the chain's record)
+        if (i == a.nsteps - 1) {
+          const int t_hi = __ffs(~a.ihi) - 1;
+#pragma unroll 1
+          for (int jj = 1; jj <= a.hi_checks; ++jj) {
+            const bool act = jj <= t_hi;
+            const int sl = __popc(a.ihi - (1 << jj) + 1);
+            const float* km = a.hck + (size_t)(2 * sl) * kRecStride;
+            const float* kr = km + kRecStride;
+            float s2[2] = {0.f, 0.f};
+            if (act) {
+              for_chunks([&](auto off, auto nn) {
+                constexpr int OFF = decltype(off)::value, N = decltype(nn)::value;
+                float vm[N], vr[N];
+                rec_ld<OFF, N>(km, vm);
+                rec_ld<OFF, N>(kr, vr);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                  const float diff = rho[OFF + j] - vr[j];
+                  s2[0] = fmaf(diff, vm[j], s2[0]);
+                  s2[1] = fmaf(diff, m[OFF + j], s2[1]);
+                }
+              });
+            }
+            cx.reduce<2>(s2);
+            ok = ok && (!act || ((s2[0] >= 0.f) && (s2[1] >= 0.f)));
+          }
+        }
       }
     }
     pf.mark(5);
@@ -234,6 +320,7 @@ __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM
         seg_st26(a.bx, cl, x);
         seg_st26(a.bg, cl, g);
         blp = slp; ben = en;
+        took = true;
       }
     }
     bw = w_new;
@@ -246,7 +333,7 @@ __device__ __forceinline__ void nuts_subtree(Ctx& cx, Shared& sh, float (*lu)[kM
     pf.leaf();
   }
   st.slp = slp; st.blp = blp; st.ben = ben; st.bw = bw; st.esum_sub = esum_sub;
-  st.n = n; st.c_prev = c_prev; st.nd = nd;
+  st.n = n; st.c_prev = c_prev; st.nd = nd; st.took = took;
 }
 
 }  // namespace tile
