@@ -64,6 +64,8 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
 // pb2_tile.cu (tcgen05 128-chain tiles, dense Gaussian)
 bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p);
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
+// pb2_tile_nuts.cu (64-chain tiles: lock-step and asynchronous-lane NUTS)
+int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p);
 
 // pb2_misc.cu
 int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);

@@ -64,8 +64,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // ---- TMEM <-> registers: N consecutive 32-bit columns of this thread's lane
 template <int N>
 __device__ __forceinline__ void tmem_st(uint32_t a, const uint32_t (&v)[N]) {
-  static_assert(N == 16 || N == 8 || N == 2, "chunk sizes used by the tile kernels");
-  if constexpr (N == 16) {
+  static_assert(N == 16 || N == 8 || N == 4 || N == 2 || N == 1, "chunk sizes used by the tile kernels");
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+  } else if constexpr (N == 1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(v[0]) : "memory");
+  } else if constexpr (N == 16) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a),
         "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
@@ -82,8 +87,15 @@ __device__ __forceinline__ void tmem_st(uint32_t a, const uint32_t (&v)[N]) {
 
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t a, uint32_t (&v)[N]) {   // caller issues tcgen05.wait::ld
-  static_assert(N == 16 || N == 8 || N == 2, "chunk sizes used by the tile kernels");
-  if constexpr (N == 16) {
+  static_assert(N == 16 || N == 8 || N == 4 || N == 2 || N == 1, "chunk sizes used by the tile kernels");
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(a)
+                 : "memory");
+  } else if constexpr (N == 1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(a) : "memory");
+  } else if constexpr (N == 16) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
