@@ -458,6 +458,25 @@ enum { kLaneNone = 0, kLaneStart = 1, kLaneChunk = 2 };
 // max_depth - 5 per-lane slots of chunk-first leaves (m, rho)
 enum { kAOx = 0, kAOm, kAOg, kACx, kACg, kARho, kABx, kABg, kACkM, kACkR = kACkM + kS0, kAHiM = kACkR + kS0 };
 
+// FIFO of chains waiting for their next transition (ring buffer of B chain ids, -1 = empty slot): a lane hands its
+// chain back after every transition and takes the chain at the head, so all chains advance at the same pace and
+// every lane stays busy until the launch's last transitions (a chain's state between transitions is just x, g, lp
+// in the chain-state arrays).
+struct AsyncQueue {
+  int* q;                      // [B]
+  unsigned long long* ctl;     // head, tail, finished chains
+  int* t_next;                 // [B] next transition of each chain
+};
+enum { kQHead = 0, kQTail = 1, kQDone = 2 };
+
+__global__ void tile_async_init_kernel(AsyncQueue aq, int B, int t0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) { aq.ctl[kQHead] = 0ull; aq.ctl[kQTail] = (unsigned long long)B; aq.ctl[kQDone] = 0ull; }
+  if (c >= B) return;
+  aq.q[c] = c;
+  aq.t_next[c] = t0;
+}
+
 static int async_scratch_vectors(int max_depth) {
   const int nhi = max_depth > kS0 ? max_depth - kS0 : 0;
   return kAHiM + 2 * nhi;
@@ -465,12 +484,13 @@ static int async_scratch_vectors(int max_depth) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float* __restrict__ scratch_all,
-                       int* __restrict__ next_chain) {
+                       const AsyncQueue aq) {
   extern __shared__ __align__(128) unsigned char planes[];
   __shared__ Shared sh;
   __shared__ float lu[4][kM];
   __shared__ int new_chain[kM];
-  __shared__ int hi_max;
+  __shared__ int hi_max, n_need, n_got;
+  __shared__ unsigned long long q_head;
   Ctx cx;
   float* const dyn = reinterpret_cast<float*>(planes + 2 * kPlaneBytes);
   cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D);
@@ -492,8 +512,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   const uint64_t Bg = (uint64_t)p.B_global;
 
   // ---- lane state
-  int c = blockIdx.x * kM + cl;
-  if (c >= p.B) c = -1;
+  int c = -1;
   int t = p.t0;
   int type = kLaneNone;
   bool fin = false;            // the transition is complete; results are emitted at the end of the chunk
@@ -504,10 +523,10 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   LaneSub st;
   st.slp = st.blp = st.ben = st.bw = st.esum_sub = 0.f; st.n = 0; st.alive = false; st.nd = true;
   float eps_abs = 0.f, eps = 0.f;
-  unsigned long long nleap_total = 0;
   float x[kK], m[kK], g[kK], rho[kK];
 #pragma unroll
   for (int j = 0; j < kK; ++j) { x[j] = 0.f; m[j] = 0.f; g[j] = 0.f; rho[j] = 0.f; }
+  const unsigned long long Bq = (unsigned long long)p.B;
 
   // per-transition key schedule of this lane
   auto keys = [&](const uint32_t*& sk, const uint32_t*& hdr, const uint32_t*& ku) {
@@ -630,24 +649,66 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
     }
   };
 
-  // ---- prologue: the first chains of this tile
-  {
-    const bool go = c >= 0;
-    tile_load(p.x, go ? c : 0, D, cx.part, go, x);
-    tile_load(p.g, go ? c : 0, D, cx.part, go, g);
-    if (go) {
-      lp = p.lp[c];
-      eps_abs = p.step_kind == 0 ? p.step[0] : p.step[c];
-    }
-    start_transitions(go);
-  }
-
   while (true) {
+    // ------------------------------------------------------------ idle lanes take the chains at the head of the FIFO
+    {
+      if (threadIdx.x == 0) { n_need = 0; hi_max = 0; }
+      __syncthreads();
+      const bool want = type == kLaneNone;
+      int my_idx = -1;
+      if (want && cx.part == 0) my_idx = atomicAdd(&n_need, 1);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int got = 0;
+        unsigned long long h = 0;
+        volatile unsigned long long* ctl = aq.ctl;
+        while (n_need > 0) {
+          h = ctl[kQHead];
+          const long long av = (long long)(ctl[kQTail] - h);
+          if (av <= 0) break;
+          const int n = (int)(av < n_need ? av : n_need);
+          if (atomicCAS(aq.ctl + kQHead, h, h + (unsigned long long)n) == h) { got = n; break; }
+        }
+        n_got = got; q_head = h;
+      }
+      __syncthreads();
+      if (want && cx.part == 0) {
+        int nc = -1;
+        if (my_idx < n_got) {
+          volatile int* slot = aq.q + (size_t)((q_head + (unsigned long long)my_idx) % Bq);
+          while ((nc = *slot) < 0) {}   // the pusher reserved the slot before it wrote the id
+          *slot = -1;
+        }
+        new_chain[cl] = nc;
+      }
+      __threadfence();
+      __syncthreads();
+      bool go = false;
+      if (want) {
+        c = new_chain[cl];
+        if (c >= 0) {
+#pragma unroll
+          for (int j = 0; j < kK; ++j) {
+            const bool in = kK * cx.part + j < D;
+            x[j] = in ? __ldcg(p.x + (size_t)c * D + kK * cx.part + j) : 0.f;
+            g[j] = in ? __ldcg(p.g + (size_t)c * D + kK * cx.part + j) : 0.f;
+          }
+          lp = __ldcg(p.lp + c);
+          eps_abs = p.step_kind == 0 ? p.step[0] : p.step[c];
+          t = __ldcg(aq.t_next + c);
+          go = true;
+        }
+      }
+      start_transitions(go);
+    }
     // ------------------------------------------------------------ chunk set-up
-    if (threadIdx.x == 0) hi_max = 0;
     const int has_start = __syncthreads_or(type == kLaneStart ? 1 : 0);
     const int any_work = __syncthreads_or(type != kLaneNone ? 1 : 0);
-    if (!any_work) break;
+    if (!any_work) {
+      if (*(volatile unsigned long long*)(aq.ctl + kQDone) >= Bq) break;
+      __nanosleep(5000);
+      continue;
+    }
     const uint32_t *sk, *hdr, *ku;
     keys(sk, hdr, ku);
     const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)(c >= 0 ? c : 0);
@@ -686,18 +747,16 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
       if (type == kLaneChunk && !endd) ihi += 1;
       doubling_boundary(endd, true);
     }
-    // finished transitions: results (nuts.py:424-445; the next state is the trajectory candidate), next transition
+    // finished transitions: results (nuts.py:424-445; the next state is the trajectory candidate); the chain goes
+    // back to the FIFO
     {
       const bool done = fin && type != kLaneNone;
-      bool need_chain = false;
       if (done) {
         seg_ldv(sv(kACx), cl, x);
         seg_ldv(sv(kACg), cl, g);
         lp = clp;
         const int leap = nleap * p.unrolled;
-        nleap_total += (unsigned long long)leap;
         const float lar = logf(esum / (float)nleap);
-        if (cx.part == 0 && p.lar_last) p.lar_last[c] = lar;
         const int r = nuts_result_index(p, t);
         if (r >= 0) {
           const Trace& tr = p.tr;
@@ -716,41 +775,25 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
           }
         }
         t += 1;
-        if (t >= p.t1) {
-          tile_store(p.x, 0, p.B, c, D, cx.part, true, x);
-          tile_store(p.g, 0, p.B, c, D, cx.part, true, g);
-          if (cx.part == 0) {
-            p.lp[c] = lp;
-            if (p.leapfrog_total) p.leapfrog_total[c] += nleap_total;
-          }
-          nleap_total = 0;
-          need_chain = true;
-          type = kLaneNone; fin = false; st.alive = false;
+        tile_store(p.x, 0, p.B, c, D, cx.part, true, x);
+        tile_store(p.g, 0, p.B, c, D, cx.part, true, g);
+        if (cx.part == 0) {
+          p.lp[c] = lp;
+          aq.t_next[c] = t;
+          if (p.leapfrog_total) atomicAdd(p.leapfrog_total + c, (unsigned long long)leap);
+        }
+        type = kLaneNone; fin = false; st.alive = false;
+      }
+      __threadfence();
+      __syncthreads();   // all eight parts of every finished chain have written its state
+      if (done && cx.part == 0) {
+        if (t < p.t1) {
+          const unsigned long long sl = atomicAdd(aq.ctl + kQTail, 1ull);
+          *(volatile int*)(aq.q + (size_t)(sl % Bq)) = c;
+        } else {
+          atomicAdd(aq.ctl + kQDone, 1ull);
         }
       }
-      // lanes whose chain is complete take the next unprocessed chain (chains beyond the first grid * 64)
-      if (cx.part == 0) {
-        int nc = -1;
-        if (need_chain) {
-          nc = atomicAdd(next_chain, 1);
-          if (nc >= p.B) nc = -1;
-        }
-        new_chain[cl] = nc;
-      }
-      __syncthreads();
-      bool go = done && !need_chain;
-      if (need_chain) {
-        c = new_chain[cl];
-        if (c >= 0) {
-          tile_load(p.x, c, D, cx.part, true, x);
-          tile_load(p.g, c, D, cx.part, true, g);
-          lp = p.lp[c];
-          eps_abs = p.step_kind == 0 ? p.step[0] : p.step[c];
-          t = p.t0;
-          go = true;
-        }
-      }
-      start_transitions(go);
     }
   }
   cx.finish();
@@ -792,19 +835,22 @@ int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p) {
   // fused multi-transition runs: every lane at its own position of its own tree
   if (ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 && p.max_depth > kS0) {
     const int agrid = std::min(ntiles, getenv("PB2_ASYNC_GRID") ? atoi(getenv("PB2_ASYNC_GRID")) : ctx->num_sms);
-    const size_t scr_bytes = ((size_t)agrid * async_scratch_vectors(p.max_depth) * kVS * sizeof(float) + 255) & ~(size_t)255;
-    if (int rc = ensure_scratch(ctx, scr_bytes + 256, "cudaMalloc(tile async scratch)")) return rc;
-    int* next_chain = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ctx->d_ckpt) + scr_bytes);
-    const int first_free = agrid * kM;
-    if (int rc = check_cuda(ctx, cudaMemcpyAsync(next_chain, &first_free, sizeof(int), cudaMemcpyHostToDevice, ctx->stream),
-                            "cudaMemcpyAsync(next_chain)"))
-      return rc;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t scr_bytes = up((size_t)agrid * async_scratch_vectors(p.max_depth) * kVS * sizeof(float));
+    const size_t q_bytes = up((size_t)p.B * sizeof(int));
+    if (int rc = ensure_scratch(ctx, scr_bytes + 2 * q_bytes + 256, "cudaMalloc(tile async scratch)")) return rc;
+    unsigned char* base = reinterpret_cast<unsigned char*>(ctx->d_ckpt);
+    AsyncQueue aq;
+    aq.q = reinterpret_cast<int*>(base + scr_bytes);
+    aq.t_next = reinterpret_cast<int*>(base + scr_bytes + q_bytes);
+    aq.ctl = reinterpret_cast<unsigned long long*>(base + scr_bytes + 2 * q_bytes);
+    tile_async_init_kernel<<<(p.B + 255) / 256, 256, 0, ctx->stream>>>(aq, p.B, p.t0);
     if (int rc = check_cuda(ctx, cudaFuncSetAttribute(tile_nuts_async_kernel,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(tile_nuts_async)"))
       return rc;
-    tile_nuts_async_kernel<<<agrid, kThreads, smem, ctx->stream>>>(p, tp, ctx->d_ckpt, next_chain);
-    ctx->launches += 1;
+    tile_nuts_async_kernel<<<agrid, kThreads, smem, ctx->stream>>>(p, tp, ctx->d_ckpt, aq);
+    ctx->launches += 2;
     dump_tile_prof(ctx);
     return check_cuda(ctx, cudaGetLastError(), "tile_nuts_async_kernel");
   }
