@@ -705,7 +705,10 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
     const int has_start = __syncthreads_or(type == kLaneStart ? 1 : 0);
     const int any_work = __syncthreads_or(type != kLaneNone ? 1 : 0);
     if (!any_work) {
-      if (*(volatile unsigned long long*)(aq.ctl + kQDone) >= Bq) break;
+      // one thread decides for the CTA (the counter may change between two threads' reads)
+      const int all_done =
+          __syncthreads_or(threadIdx.x == 0 && *(volatile unsigned long long*)(aq.ctl + kQDone) >= Bq ? 1 : 0);
+      if (all_done) break;
       __nanosleep(5000);
       continue;
     }
@@ -757,6 +760,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
         lp = clp;
         const int leap = nleap * p.unrolled;
         const float lar = logf(esum / (float)nleap);
+        if (cx.part == 0 && p.lar_last) p.lar_last[c] = lar;
         const int r = nuts_result_index(p, t);
         if (r >= 0) {
           const Trace& tr = p.tr;
@@ -832,8 +836,9 @@ int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p) {
   // P hi/lo planes + the previous leaf's checkpoint (momentum, rho) + the gradient exchange buffer
   const size_t smem = 2 * (size_t)kPlaneBytes + (2 * kVS + kXbufFloats) * sizeof(float);
   const int ntiles = (p.B + kM - 1) / kM;
-  // fused multi-transition runs: every lane at its own position of its own tree
-  if (ctx->dense_variant != 3 && p.lar_last == nullptr && p.t1 - p.t0 >= 2 && p.max_depth > kS0) {
+  // every lane at its own position of its own tree (the lock-step kernel remains as the literal batched algorithm:
+  // dense_variant 3, or max_tree_depth <= 5)
+  if (ctx->dense_variant != 3 && p.max_depth > kS0) {
     const int agrid = std::min(ntiles, getenv("PB2_ASYNC_GRID") ? atoi(getenv("PB2_ASYNC_GRID")) : ctx->num_sms);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t scr_bytes = up((size_t)agrid * async_scratch_vectors(p.max_depth) * kVS * sizeof(float));
