@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libpb2.so')
+LIB_PATH = os.environ.get('PB2_LIB_PATH') or os.path.join(_HERE, '_C', 'libpb2.so')   # override: A/B builds
 
 PB2_OK = 0
 LAYOUT_PARTITIONABLE = 0

@@ -489,7 +489,8 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   __shared__ Shared sh;
   __shared__ float lu[4][kM];
   __shared__ int new_chain[kM];
-  __shared__ int hi_max, n_need, n_got;
+  __shared__ int hi_max, n_need, n_got, n_start;
+  __shared__ int st_lane[kM], st_c[kM], st_t[kM];
   __shared__ unsigned long long q_head;
   Ctx cx;
   float* const dyn = reinterpret_cast<float*>(planes + 2 * kPlaneBytes);
@@ -567,15 +568,28 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   // ---- start transition t of chain c from (x, g, lp): _start_trajectory_batched (nuts.py:512-539).  Tile-uniform
   // (one cross-part reduction); `go` selects the lanes that start.
   auto start_transitions = [&](bool go) {
+    // momentum ~ N(0, I).  After the first chunk only a few lanes start at a time: their draws are spread over the
+    // whole CTA and handed over through shared memory (the previous-leaf checkpoint buffer is dead between chunks)
+    if (threadIdx.x == 0) n_start = 0;
+    __syncthreads();
+    if (go && cx.part == 0) {
+      const int idx = atomicAdd(&n_start, 1);
+      st_lane[idx] = cl; st_c[idx] = c; st_t[idx] = t;
+    }
+    __syncthreads();
+    float* const mom = dyn;   // [kKP][kM]
+    for (int w = threadIdx.x; w < n_start * D; w += kThreads) {
+      const int li = w / D, d = w - li * D;
+      const uint32_t* skl = p.sched + (size_t)(st_t[li] - p.t_sched0) * p.sched_stride;
+      mom[d * kM + st_lane[li]] = nuts_momentum(p, skl, (uint64_t)p.chain_offset + (uint64_t)st_c[li], d);
+    }
+    __syncthreads();
     float s1[1] = {0.f};
     if (go) {
-      const uint32_t *sk, *hdr, *ku;
-      keys(sk, hdr, ku);
-      const uint64_t cg = (uint64_t)p.chain_offset + (uint64_t)c;
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
         const int d = kK * cx.part + j;
-        const float mm = d < D ? nuts_momentum(p, sk, cg, d) : 0.f;
+        const float mm = d < D ? mom[d * kM + cl] : 0.f;
         m[j] = mm;
         s1[0] = fmaf(mm, mm, s1[0]);
       }
@@ -701,6 +715,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
       }
       start_transitions(go);
     }
+    pf.mark(10);
     // ------------------------------------------------------------ chunk set-up
     const int has_start = __syncthreads_or(type == kLaneStart ? 1 : 0);
     const int any_work = __syncthreads_or(type != kLaneNone ? 1 : 0);
@@ -741,15 +756,20 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
       nuts_leaf(cx, e, i, 0u, act, jmax, hi_slot_w, ihi, t_hi, i == kChunkTicks - 1 ? hi_checks : 0, eps, H0, lu[i & 3],
                 x, m, g, rho, st, pf);
       // START lanes: doublings 0..3 end after ticks 1, 3, 7, 15
-      if (has_start && i >= 1 && i < kChunkTicks - 1 && ((i + 1) & i) == 0)
+      if (has_start && i >= 1 && i < kChunkTicks - 1 && ((i + 1) & i) == 0) {
+        pf.mark(0);
         doubling_boundary(type == kLaneStart && !fin, false);
+        pf.mark(7);
+      }
     }
+    pf.mark(0);
     // ------------------------------------------------------------ end of the chunk
     {
       const bool endd = !fin && (type == kLaneStart || (type == kLaneChunk && (!st.alive || ihi + 1 == nchunks)));
       if (type == kLaneChunk && !endd) ihi += 1;
       doubling_boundary(endd, true);
     }
+    pf.mark(8);
     // finished transitions: results (nuts.py:424-445; the next state is the trajectory candidate); the chain goes
     // back to the FIFO
     {
@@ -799,6 +819,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
         }
       }
     }
+    pf.mark(9);
   }
   cx.finish();
 }
@@ -808,10 +829,11 @@ static void dump_tile_prof(pb2_ctx* ctx) {
   unsigned long long h[2][16];
   cudaStreamSynchronize(ctx->stream);
   cudaMemcpyFromSymbol(h, g_tile_prof, sizeof(h));
-  static const char* nm[7] = {"head", "kick+stage", "contract", "post", "reduce4", "extra checks", "scalars+take"};
+  static const char* nm[11] = {"head", "kick+stage", "contract", "post", "reduce4", "extra checks", "scalars+take",
+                               "START boundaries", "chunk-end boundary", "finish", "acquire+start"};
   for (int w = 0; w < 2; ++w) {
     fprintf(stderr, "[tileprof t%d] leaves %llu:", w ? 511 : 0, h[w][15]);
-    for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.0f", nm[k], h[w][15] ? (double)h[w][k] / h[w][15] : 0.0);
+    for (int k = 0; k < 11; ++k) fprintf(stderr, " %s %.0f", nm[k], h[w][15] ? (double)h[w][k] / h[w][15] : 0.0);
     fprintf(stderr, "\n");
   }
   unsigned long long z[2][16] = {};
