@@ -463,18 +463,18 @@ enum { kAOx = 0, kAOm, kAOg, kACx, kACg, kARho, kABx, kABg, kACkM, kACkR = kACkM
 // every lane stays busy until the launch's last transitions (a chain's state between transitions is just x, g, lp
 // in the chain-state arrays).
 struct AsyncQueue {
-  int* q;                      // [B]
-  unsigned long long* ctl;     // head, tail, finished chains
+  int* q;                      // [cap] ring of chain ids, -1 = empty slot
+  unsigned long long* ctl;     // head (next ticket), tail (next push)
   int* t_next;                 // [B] next transition of each chain
+  int cap;                     // >= B + lanes: live tickets (waiting lanes + queued chains) never share a slot
 };
 enum { kQHead = 0, kQTail = 1, kQDone = 2 };
 
 __global__ void tile_async_init_kernel(AsyncQueue aq, int B, int t0) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0) { aq.ctl[kQHead] = 0ull; aq.ctl[kQTail] = (unsigned long long)B; aq.ctl[kQDone] = 0ull; }
-  if (c >= B) return;
-  aq.q[c] = c;
-  aq.t_next[c] = t0;
+  if (c < aq.cap) aq.q[c] = c < B ? c : -1;
+  if (c < B) aq.t_next[c] = t0;
 }
 
 static int async_scratch_vectors(int max_depth) {
@@ -489,9 +489,8 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   __shared__ Shared sh;
   __shared__ float lu[4][kM];
   __shared__ int new_chain[kM];
-  __shared__ int hi_max, n_need, n_got, n_start;
+  __shared__ int hi_max, n_start;
   __shared__ int st_lane[kM], st_c[kM], st_t[kM];
-  __shared__ unsigned long long q_head;
   Ctx cx;
   float* const dyn = reinterpret_cast<float*>(planes + 2 * kPlaneBytes);
   cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D);
@@ -527,7 +526,9 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   float x[kK], m[kK], g[kK], rho[kK];
 #pragma unroll
   for (int j = 0; j < kK; ++j) { x[j] = 0.f; m[j] = 0.f; g[j] = 0.f; rho[j] = 0.f; }
-  const unsigned long long Bq = (unsigned long long)p.B;
+  const unsigned long long qcap = (unsigned long long)aq.cap;
+  const long long total_pushes = (long long)p.B * (long long)(p.t1 - p.t0);
+  long long ticket = -1;   // (part 0 of a lane) my position in the FIFO while the lane waits for a chain
 
   // per-transition key schedule of this lane
   auto keys = [&](const uint32_t*& sk, const uint32_t*& hdr, const uint32_t*& ku) {
@@ -584,6 +585,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
       mom[d * kM + st_lane[li]] = nuts_momentum(p, skl, (uint64_t)p.chain_offset + (uint64_t)st_c[li], d);
     }
     __syncthreads();
+    pf.mark(12);
     float s1[1] = {0.f};
     if (go) {
 #pragma unroll
@@ -665,38 +667,23 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
 
   while (true) {
     // ------------------------------------------------------------ idle lanes take the chains at the head of the FIFO
+    // A lane without a chain draws a TICKET (its position in the FIFO, one atomicAdd) and looks at that slot once
+    // per chunk: no lane ever spins and nobody needs the tail.  Tickets beyond the total number of pushes
+    // (every chain is pushed once per transition) will never be served: the lane retires.
     {
-      if (threadIdx.x == 0) { n_need = 0; hi_max = 0; }
-      __syncthreads();
+      if (threadIdx.x == 0) hi_max = 0;
       const bool want = type == kLaneNone;
-      int my_idx = -1;
-      if (want && cx.part == 0) my_idx = atomicAdd(&n_need, 1);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int got = 0;
-        unsigned long long h = 0;
-        volatile unsigned long long* ctl = aq.ctl;
-        while (n_need > 0) {
-          h = ctl[kQHead];
-          const long long av = (long long)(ctl[kQTail] - h);
-          if (av <= 0) break;
-          const int n = (int)(av < n_need ? av : n_need);
-          if (atomicCAS(aq.ctl + kQHead, h, h + (unsigned long long)n) == h) { got = n; break; }
-        }
-        n_got = got; q_head = h;
-      }
-      __syncthreads();
       if (want && cx.part == 0) {
+        if (ticket < 0) ticket = (long long)atomicAdd(aq.ctl + kQHead, 1ull);
         int nc = -1;
-        if (my_idx < n_got) {
-          volatile int* slot = aq.q + (size_t)((q_head + (unsigned long long)my_idx) % Bq);
-          while ((nc = *slot) < 0) {}   // the pusher reserved the slot before it wrote the id
-          *slot = -1;
+        if (ticket < total_pushes) {
+          volatile int* slot = aq.q + (size_t)((unsigned long long)ticket % qcap);
+          nc = *slot;
+          if (nc >= 0) { *slot = -1; ticket = -1; }
         }
         new_chain[cl] = nc;
       }
-      __threadfence();
-      __syncthreads();
+      __syncthreads();   // (the chain's state is read with ld.cg from L2, where its last owner's fenced stores are)
       bool go = false;
       if (want) {
         c = new_chain[cl];
@@ -713,6 +700,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
           go = true;
         }
       }
+      pf.mark(11);
       start_transitions(go);
     }
     pf.mark(10);
@@ -720,11 +708,10 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
     const int has_start = __syncthreads_or(type == kLaneStart ? 1 : 0);
     const int any_work = __syncthreads_or(type != kLaneNone ? 1 : 0);
     if (!any_work) {
-      // one thread decides for the CTA (the counter may change between two threads' reads)
-      const int all_done =
-          __syncthreads_or(threadIdx.x == 0 && *(volatile unsigned long long*)(aq.ctl + kQDone) >= Bq ? 1 : 0);
-      if (all_done) break;
-      __nanosleep(5000);
+      // lanes that still hold a servable ticket wait for their chain; otherwise every lane of the tile has retired
+      const int pending = __syncthreads_or(cx.part == 0 && ticket >= 0 && ticket < total_pushes ? 1 : 0);
+      if (!pending) break;
+      __nanosleep(2000);
       continue;
     }
     const uint32_t *sk, *hdr, *ku;
@@ -810,13 +797,9 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
       }
       __threadfence();
       __syncthreads();   // all eight parts of every finished chain have written its state
-      if (done && cx.part == 0) {
-        if (t < p.t1) {
-          const unsigned long long sl = atomicAdd(aq.ctl + kQTail, 1ull);
-          *(volatile int*)(aq.q + (size_t)(sl % Bq)) = c;
-        } else {
-          atomicAdd(aq.ctl + kQDone, 1ull);
-        }
+      if (done && cx.part == 0 && t < p.t1) {
+        const unsigned long long sl = atomicAdd(aq.ctl + kQTail, 1ull);
+        *(volatile int*)(aq.q + (size_t)(sl % qcap)) = c;
       }
     }
     pf.mark(9);
@@ -829,11 +812,11 @@ static void dump_tile_prof(pb2_ctx* ctx) {
   unsigned long long h[2][16];
   cudaStreamSynchronize(ctx->stream);
   cudaMemcpyFromSymbol(h, g_tile_prof, sizeof(h));
-  static const char* nm[11] = {"head", "kick+stage", "contract", "post", "reduce4", "extra checks", "scalars+take",
-                               "START boundaries", "chunk-end boundary", "finish", "acquire+start"};
+  static const char* nm[13] = {"head", "kick+stage", "contract", "post", "reduce4", "extra checks", "scalars+take",
+                               "START boundaries", "chunk-end boundary", "finish", "start(rest)", "acquire", "momentum"};
   for (int w = 0; w < 2; ++w) {
     fprintf(stderr, "[tileprof t%d] leaves %llu:", w ? 511 : 0, h[w][15]);
-    for (int k = 0; k < 11; ++k) fprintf(stderr, " %s %.0f", nm[k], h[w][15] ? (double)h[w][k] / h[w][15] : 0.0);
+    for (int k = 0; k < 13; ++k) fprintf(stderr, " %s %.0f", nm[k], h[w][15] ? (double)h[w][k] / h[w][15] : 0.0);
     fprintf(stderr, "\n");
   }
   unsigned long long z[2][16] = {};
@@ -864,14 +847,15 @@ int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p) {
     const int agrid = std::min(ntiles, getenv("PB2_ASYNC_GRID") ? atoi(getenv("PB2_ASYNC_GRID")) : ctx->num_sms);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t scr_bytes = up((size_t)agrid * async_scratch_vectors(p.max_depth) * kVS * sizeof(float));
-    const size_t q_bytes = up((size_t)p.B * sizeof(int));
+    AsyncQueue aq;
+    aq.cap = p.B + agrid * kM + 64;
+    const size_t q_bytes = up((size_t)aq.cap * sizeof(int));
     if (int rc = ensure_scratch(ctx, scr_bytes + 2 * q_bytes + 256, "cudaMalloc(tile async scratch)")) return rc;
     unsigned char* base = reinterpret_cast<unsigned char*>(ctx->d_ckpt);
-    AsyncQueue aq;
     aq.q = reinterpret_cast<int*>(base + scr_bytes);
     aq.t_next = reinterpret_cast<int*>(base + scr_bytes + q_bytes);
     aq.ctl = reinterpret_cast<unsigned long long*>(base + scr_bytes + 2 * q_bytes);
-    tile_async_init_kernel<<<(p.B + 255) / 256, 256, 0, ctx->stream>>>(aq, p.B, p.t0);
+    tile_async_init_kernel<<<(aq.cap + 255) / 256, 256, 0, ctx->stream>>>(aq, p.B, p.t0);
     if (int rc = check_cuda(ctx, cudaFuncSetAttribute(tile_nuts_async_kernel,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(tile_nuts_async)"))

@@ -560,13 +560,14 @@ def test_tile_nuts_matches_oracle_and_warp_kernel(tfp, depth, eps):
   assert (outs[0][1].leapfrogs_taken == outs[1][1].leapfrogs_taken).float().mean() > 0.97
 
 
-@pytest.mark.parametrize('B,depth', [(1000, 7), (4096, 10)])
-def test_tile_nuts_doubling_scheduler_is_bit_identical_to_lockstep(tfp, B, depth):
-  """Multi-transition fused NUTS on the dense target runs the doubling-task scheduler
-  (pb2_tile_sched.cuh): chains are regrouped into 128-chain tiles per tree doubling.  Because every
-  random draw is keyed by (step seed, global chain index) and each chain's arithmetic is independent
-  of its tile mates, the result must equal the lock-step tile kernel's bit for bit -- and a ragged B
-  (1000 = 7 tiles + 104) exercises partially filled tiles."""
+@pytest.mark.parametrize('B,depth', [(1000, 7), (4096, 10), (10000, 10)])
+def test_tile_nuts_async_lanes_are_bit_identical_to_lockstep(tfp, B, depth):
+  """NUTS on the dense target runs the asynchronous-lane tile kernel (pb2_tile_nuts.cu): every lane of a
+  64-chain tile is at its own leaf of its own tree / transition, chains go back to a FIFO after every
+  transition.  Because every random draw is keyed by (step seed, global chain index) and each chain's
+  arithmetic is independent of its tile mates, the result must equal the lock-step tile kernel's (the
+  reference's literal batched algorithm) bit for bit -- ragged B (partially filled tiles) and more chains
+  than lanes (10000 > 148 * 64: chains queue for lanes) included -- and must not depend on scheduling."""
   from probability_b200 import _lib
   tg, _, x0 = _dense100_state(B, seed=3)
   ctx = _lib.Context.get(dev())
@@ -575,16 +576,28 @@ def test_tile_nuts_doubling_scheduler_is_bit_identical_to_lockstep(tfp, B, depth
                           kr.has_divergence, kr.reach_max_depth, kr.log_accept_ratio)
   outs = {}
   try:
-    for name, variant in (('sched', 0), ('lockstep', 3), ('sched_again', 0)):
+    for name, variant in (('async', 0), ('lockstep', 3), ('async_again', 0)):
       ctx.set_int('dense_variant', variant)
       res = tfp.mcmc.sample_chain(5, t(x0), kernel=k, trace_fn=fields, seed=7)
       outs[name] = [res.all_states.cpu().numpy()] + [f.cpu().numpy() for f in res.trace]
   finally:
     ctx.set_int('dense_variant', 0)
-  for a, b in zip(outs['sched'], outs['lockstep']):
+  for a, b in zip(outs['async'], outs['lockstep']):
     np.testing.assert_array_equal(a, b)
-  for a, b in zip(outs['sched'], outs['sched_again']):
+  for a, b in zip(outs['async'], outs['async_again']):
     np.testing.assert_array_equal(a, b)
-  assert np.isfinite(outs['sched'][0]).all() and np.isfinite(outs['sched'][3]).all()
-  lf = outs['sched'][1]
+  assert np.isfinite(outs['async'][0]).all() and np.isfinite(outs['async'][3]).all()
+  lf = outs['async'][1]
   assert lf.min() >= 1 and lf.max() <= 2 ** depth - 1 and len(np.unique(lf)) > 3
+
+
+def test_tile_nuts_async_single_transitions_equal_fused_run(tfp):
+  """A python loop over one_step (one launch per transition: the path of a per-step host loop and of step-size
+  adaptation) == one fused K-transition launch, on the asynchronous-lane kernel."""
+  tg, _, x0 = _dense100_state(700, seed=4)
+  k = tfp.mcmc.NoUTurnSampler(tg, step_size=0.7, max_tree_depth=8)
+  fused = tfp.mcmc.sample_chain(4, t(x0), kernel=k, trace_fn=lambda _, kr: kr.leapfrogs_taken, seed=11)
+  # a trace_fn that computes on values cannot be fused: sample_chain falls back to its one_step loop
+  loop = tfp.mcmc.sample_chain(4, t(x0), kernel=k, trace_fn=lambda _, kr: kr.leapfrogs_taken + 0, seed=11)
+  np.testing.assert_array_equal(loop.all_states.cpu().numpy(), fused.all_states.cpu().numpy())
+  np.testing.assert_array_equal(loop.trace.cpu().numpy(), fused.trace.cpu().numpy())
