@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of tile_nuts_async_kernel per NUTS transition of 16,384 chains (ncu, r01)
+NCU_DRAM_BYTES_PER_TRANSITION = 6.4e8
 METRIC = 'leapfrog_grad_evals_per_sec'
 UNIT = 'grad-evals/s'
 D = 100
@@ -299,6 +301,25 @@ def main():
   else:
     e2e_value = e2e_grad / e2e_s
 
+  # ---- the same, as ONE user call: H2D initial state, sample_chain(num_results=K), D2H of all K states
+  all_pinned = torch.empty(e2e_steps, B, D, dtype=torch.float32).pin_memory()
+  tot1 = torch.zeros(B, dtype=torch.int64, device=dev)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  st = x_pinned.to(dev, non_blocking=True)
+  r = tfp.mcmc.sample_chain(e2e_steps, st, kernel=nuts, trace_fn=None, seed=300, experimental_leapfrog_total=tot1)
+  all_pinned.copy_(r, non_blocking=True)
+  torch.cuda.synchronize()
+  one_call_s = time.perf_counter() - t0
+  oc = torch.tensor([float(tot1.sum().item()), one_call_s], device=dev, dtype=torch.float64)
+  if world > 1:
+    g = [torch.zeros_like(oc) for _ in range(world)]
+    dist.all_gather(g, oc)
+    one_call_value = sum(float(v[0]) for v in g) / max(float(v[1]) for v in g)
+  else:
+    one_call_value = float(oc[0]) / float(oc[1])
+  del r
+
   # ---- min-ESS/s (second half of the metric): 200 traced draws per chain
   ess_info = None
   if not args.no_ess and rank == 0:
@@ -330,15 +351,20 @@ def main():
     return
 
   pk, pk_src = peaks()
-  # roofline of the dominant kernel (tile_nuts_sched_kernel): ALGORITHMIC flops = 2*D^2 per gradient
+  # roofline of the dominant kernel (tile_nuts_async_kernel): ALGORITHMIC flops = 2*D^2 per gradient
   # evaluation, against the dense TF32 tensor peak (= 1/2 of the measured sustained bf16 peak), DESIGN.md section 5.
   flops = 2.0 * D * D * n_grad
   avg_launch_s = total_s
   achieved = flops / avg_launch_s / 1e12
   peak = 0.5 * pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-              'traffic': None, 'peak_source': pk_src + ': 0.5 x bf16_tflops_sustained (dense TF32)',
-              'kernel': 'tile_nuts_sched_kernel (tcgen05 kind::tf32, 3xTF32 split: executes 3x the algorithmic flops)'}
+              'traffic': NCU_DRAM_BYTES_PER_TRANSITION * args.steps,
+              'traffic_source': 'ncu --set full of this kernel (profiles/r01_tile_nuts_async_ncu_full_summary.csv): '
+                                'dram read+write bytes per transition of 16,384 chains, scaled to the K of this launch',
+              'peak_source': pk_src + ': 0.5 x bf16_tflops_sustained (dense TF32)',
+              'kernel': 'tile_nuts_async_kernel (tcgen05 kind::tf32; 3xTF32 split x 112/100 padding x two half-rows per '
+                        'chain: the tensor pipe executes ~7x the algorithmic flops; ncu: tensor pipe 18.6 % active; the '
+                        'kernel is bound by the dependent latency of one leapfrog, DESIGN.md section 5)'}
   cpu_baseline = None
   if not args.no_cpu_baseline and world == 1:
     cpu_baseline, _, _ = cpu_reference_arm(3, 1, budget_s=20.0)
@@ -348,7 +374,9 @@ def main():
           'clocks': clocks, 'gpu_launches': int(launches),
           'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * D * 4,
                   'd2h_bytes_per_step': B * D * 4 + B * 4, 'steps': e2e_steps,
-                  'api': 'tfp.mcmc.sample_chain(num_results=1) per step incl. bootstrap_results'},
+                  'api': 'tfp.mcmc.sample_chain(num_results=1) per step incl. bootstrap_results',
+                  'one_call': {'value': one_call_value, 'unit': UNIT,
+                               'note': 'H2D initial state + ONE sample_chain(num_results=%d) + D2H of all states' % e2e_steps}},
           'roofline': roofline, 'cpu_baseline': cpu_baseline, 'step_size': eps,
           'leapfrogs_per_transition': n_grad / (B * args.steps),
           'per_launch_run': {'value': fused_value, 'unit': UNIT,
