@@ -70,8 +70,11 @@ int pb2_ctx_synchronize(pb2_ctx* ctx);
 const char* pb2_last_error(pb2_ctx* ctx); /* ctx may be NULL: last global error */
 /* number of pb2 kernels launched on this context since creation (bench "gpu_launches") */
 long long pb2_launch_count(pb2_ctx* ctx);
-/* tuning / A-B switches.  "dense_variant": 0 = default (128-chain tcgen05 tiles where supported, else
- * warp-per-chain), 1 = force warp-per-chain FP32-FMA kernels, 2 = half-warp-per-chain experiment. */
+/* tuning / A-B switches.  "dense_variant" (dense-Gaussian target): 0 = default (tcgen05 tile kernels where
+ * supported -- 32 < D <= 100, B >= 256: 128-chain HMC tiles, 64-chain asynchronous-lane NUTS tiles -- else
+ * warp-per-chain), 1 = force the warp-per-chain FP32-FMA kernels, 2 = half-warp-per-chain experiment,
+ * 3 = tile kernels with the lock-step NUTS kernel (the reference's literal batched algorithm; the bit-exact
+ * partner of the asynchronous-lane kernel in the tests). */
 int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value);
 
 /* ---- targets ---------------------------------------------------------------- */

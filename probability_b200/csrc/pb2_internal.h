@@ -14,7 +14,7 @@ struct pb2_ctx {
   int num_sms = 148;
   int max_smem_optin = 227 * 1024;
   long long launches = 0;
-  int dense_variant = 0;           // 0: half-warp-per-chain (default), 1: warp-per-chain (A/B profiling)
+  int dense_variant = 0;           // A/B switch of the dense-Gaussian kernels, see pb2_ctx_set_int in pb2.h
   std::string err;
   int* d_queue = nullptr;          // dynamic chain queue counter
   float* d_ckpt = nullptr;         // global checkpoint scratch (block-group targets)
@@ -61,7 +61,7 @@ int check_cuda(pb2_ctx* ctx, cudaError_t e, const char* what);
 // pb2_chain_kernels.cu
 int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io);
 
-// pb2_tile.cu (tcgen05 128-chain tiles, dense Gaussian)
+// pb2_tile.cu (tcgen05 tile kernels, dense Gaussian: dispatch + the 128-chain HMC kernel)
 bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, const ChainParams& p);
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
 // pb2_tile_nuts.cu (64-chain tiles: lock-step and asynchronous-lane NUTS)
