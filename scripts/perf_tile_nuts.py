@@ -1,4 +1,4 @@
-"""scheduler (doubling-task) tile NUTS vs lock-step tile vs warp kernels: same chains, same trees."""
+"""async-lane tile NUTS (variant 0) vs lock-step tile (3) vs warp kernels (1): same chains, same trees."""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
