@@ -137,7 +137,7 @@ def cpu_reference_arm(steps, warmup, budget_s=25.0):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=100)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours')
   ap.add_argument('--chains', type=int, default=CHAINS_PER_GPU)

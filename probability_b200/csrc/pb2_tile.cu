@@ -11,11 +11,6 @@
 namespace pb2 {
 using namespace tile;
 
-struct TileIO {
-  float x[kK];
-  float g[kK];
-};
-
 __device__ __forceinline__ void tile_load(const float* base, int c, int D, int slice, bool live, float (&v)[kK]) {
   const float* row = base + (size_t)c * D + kK * slice;
 #pragma unroll

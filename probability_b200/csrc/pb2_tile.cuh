@@ -1,4 +1,5 @@
-// Building blocks of the 128-chain TILE kernels for the dense-Gaussian target: the gradient of all
+// Building blocks of the 128-chain TILE kernels (tile_hmc_kernel, pb2_tile.cu; the NUTS kernels use the 64-chain
+// variant pb2_tile64.cuh, which reuses the helpers below) for the dense-Gaussian target: the gradient of all
 // chains of a tile is ONE tcgen05 contraction  G = -(X - mu) P  (3xTF32 split, FP32 accurate),
 //   A = (X - mu) hi/lo planes in TMEM (written by the owning threads with tcgen05.st),
 //   B = P hi/lo planes in shared memory (canonical K-major no-swizzle layout),
@@ -120,47 +121,6 @@ __device__ __forceinline__ void for_chunks(F&& f) {
   f(std::integral_constant<int, 0>{}, std::integral_constant<int, 16>{});
   f(std::integral_constant<int, 16>{}, std::integral_constant<int, 8>{});
   f(std::integral_constant<int, 24>{}, std::integral_constant<int, 2>{});
-}
-
-// ---- a thread's 26-float SEGMENT of a [kKP x kM] scratch vector (global or shared memory), laid out for
-// 128-bit accesses: the slice block (kK * kM floats) is six [kM][4] planes followed by one [kM][2] plane, so a
-// warp's float4 access covers 512 contiguous bytes.  Chunk (OFF, N) uses the same (0,16),(16,8),(24,2)
-// tiling as the TMEM accesses.
-constexpr int kSegTail = 6 * kM * 4;
-template <int OFF, int N>
-__device__ __forceinline__ void seg_ld(const float* sb, int cl, float (&v)[N]) {
-  if constexpr (N == 2) {
-    const float2 t = *reinterpret_cast<const float2*>(sb + kSegTail + cl * 2);
-    v[0] = t.x; v[1] = t.y;
-  } else {
-#pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(sb + ((OFF / 4 + q) * kM + cl) * 4);
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-  }
-}
-template <int OFF, int N>
-__device__ __forceinline__ void seg_st(float* sb, int cl, const float* v) {
-  if constexpr (N == 2) {
-    *reinterpret_cast<float2*>(sb + kSegTail + cl * 2) = make_float2(v[0], v[1]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < N / 4; ++q)
-      *reinterpret_cast<float4*>(sb + ((OFF / 4 + q) * kM + cl) * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  }
-}
-__device__ __forceinline__ void seg_ld26(const float* sb, int cl, float (&v)[kK]) {
-  float a[16], b[8], c[2];
-  seg_ld<0, 16>(sb, cl, a); seg_ld<16, 8>(sb, cl, b); seg_ld<24, 2>(sb, cl, c);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = a[j];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[16 + j] = b[j];
-  v[24] = c[0]; v[25] = c[1];
-}
-__device__ __forceinline__ void seg_st26(float* sb, int cl, const float (&v)[kK]) {
-  seg_st<0, 16>(sb, cl, v); seg_st<16, 8>(sb, cl, v + 16); seg_st<24, 2>(sb, cl, v + 24);
 }
 
 struct Shared {
@@ -305,29 +265,6 @@ struct Ctx {
     for (int j = 0; j < 8; ++j) g[16 + j] = __uint_as_float(t1[j]);
     g[24] = __uint_as_float(t2[0]);
     g[25] = __uint_as_float(t2[1]);
-  }
-
-  // one chunk of my slice of D
-  template <int OFF, int N>
-  __device__ __forceinline__ void load_d_chunk(float (&gc)[N]) {
-    uint32_t t[N];
-    tmem_ld<N>(lane_addr + kColD + kK * slice + OFF, t);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < N; ++j) gc[j] = __uint_as_float(t[j]);
-  }
-
-  // put a gradient back into my slice of D (the tile NUTS kernels keep g there, not in registers)
-  __device__ __forceinline__ void store_d(const float (&g)[kK]) {
-    const uint32_t base = lane_addr + kColD + kK * slice;
-    for_chunks([&](auto off, auto n) {
-      constexpr int OFF = decltype(off)::value, N = decltype(n)::value;
-      uint32_t t[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) t[j] = __float_as_uint(g[OFF + j]);
-      tmem_st<N>(base + OFF, t);
-    });
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
   // cross-slice sums (fixed order => the 4 threads of a chain get identical bits); one barrier

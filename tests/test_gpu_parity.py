@@ -601,3 +601,37 @@ def test_tile_nuts_async_single_transitions_equal_fused_run(tfp):
   loop = tfp.mcmc.sample_chain(4, t(x0), kernel=k, trace_fn=lambda _, kr: kr.leapfrogs_taken + 0, seed=11)
   np.testing.assert_array_equal(loop.all_states.cpu().numpy(), fused.all_states.cpu().numpy())
   np.testing.assert_array_equal(loop.trace.cpu().numpy(), fused.trace.cpu().numpy())
+
+
+@pytest.mark.parametrize('case', ['unrolled2', 'per_chain_step'])
+def test_tile_nuts_options_match_lockstep_and_oracle(tfp, case):
+  """unrolled_leapfrog_steps > 1 (nuts.py:826-843: L leapfrogs per tree leaf) and per-chain step sizes on the
+  tensor-core tile kernels: asynchronous lanes == lock-step bit for bit, and the trees match the oracle's."""
+  from probability_b200 import _lib
+  B = 640
+  tg, o32, x0 = _dense100_state(B, seed=6)
+  ctx = _lib.Context.get(dev())
+  if case == 'unrolled2':
+    eps_np, kw = np.float32(0.35), dict(unrolled_leapfrog_steps=2)
+    k = tfp.mcmc.NoUTurnSampler(tg, step_size=0.35, max_tree_depth=7, **kw)
+  else:
+    eps_np = (0.4 + 0.4 * np.random.default_rng(1).random((B, 1))).astype(np.float32)
+    kw = {}
+    k = tfp.mcmc.NoUTurnSampler(tg, step_size=t(eps_np), max_tree_depth=7)
+  seed = orng.key(21)
+  outs = {}
+  try:
+    for variant in (0, 3):
+      ctx.set_int('dense_variant', variant)
+      s, r = k.one_step(t(x0), k.bootstrap_results(t(x0)), seed=seed)
+      outs[variant] = (s.cpu().numpy(), r.leapfrogs_taken.cpu().numpy(), r.energy.cpu().numpy())
+  finally:
+    ctx.set_int('dense_variant', 0)
+  for a, b in zip(outs[0], outs[3]):
+    np.testing.assert_array_equal(a, b)
+  lp0, g0 = o32.logp_grad(x0)
+  ref = omcmc.nuts_one_step(o32, x0, lp0, g0, eps_np, seed, max_tree_depth=7, **kw)
+  same = outs[0][1] == ref['leapfrogs_taken']
+  assert same.mean() >= 0.97
+  close = np.isclose(outs[0][0], ref['state'], rtol=2e-3, atol=2e-3).all(1)
+  assert close[same].mean() >= 0.97
