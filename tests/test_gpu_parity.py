@@ -635,3 +635,28 @@ def test_tile_nuts_options_match_lockstep_and_oracle(tfp, case):
   assert same.mean() >= 0.97
   close = np.isclose(outs[0][0], ref['state'], rtol=2e-3, atol=2e-3).all(1)
   assert close[same].mean() >= 0.97
+
+
+@pytest.mark.parametrize('sampler', ['nuts', 'hmc'])
+def test_tile_kernels_chain_sharding_is_bit_identical(tfp, sampler):
+  """Chains sharded over ranks: the RNG counters use the GLOBAL chain index and the global batch size,
+  so two half-batches run with ChainShard(offset, total) reproduce the unsharded run bit for bit -- here on the
+  tensor-core tile kernels, both shards on one GPU."""
+  B = 1024
+  tg, _, x0 = _dense100_state(B, seed=8)
+
+  def run(x, shard):
+    if sampler == 'nuts':
+      k = tfp.mcmc.NoUTurnSampler(tg, step_size=0.7, max_tree_depth=8, experimental_chain_shard=shard)
+      tr = lambda _, kr: (kr.leapfrogs_taken, kr.energy)
+    else:
+      k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.5, num_leapfrog_steps=6, experimental_chain_shard=shard)
+      tr = lambda _, kr: (kr.is_accepted, kr.log_accept_ratio)
+    r = tfp.mcmc.sample_chain(3, t(x), kernel=k, trace_fn=tr, seed=13)
+    return [r.all_states.cpu().numpy()] + [f.cpu().numpy() for f in r.trace]
+
+  full = run(x0, None)
+  lo = run(x0[:B // 2], tfp.mcmc.ChainShard(0, B))
+  hi = run(x0[B // 2:], tfp.mcmc.ChainShard(B // 2, B))
+  for f, a, b in zip(full, lo, hi):
+    np.testing.assert_array_equal(f, np.concatenate([a, b], axis=1))
