@@ -67,6 +67,8 @@ class ClockSampler:
     self.lines = []
 
   def start(self):
+    if os.environ.get('PB2_BENCH_NO_SMI'):   # diagnosis only: does the poller perturb the measurement?
+      return
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
@@ -78,15 +80,21 @@ class ClockSampler:
 
   def _read(self):
     for ln in self.proc.stdout:
-      self.lines.append(ln.strip())
+      self.lines.append((time.time(), ln.strip()))
 
-  def stop(self):
+  def stop(self, t_begin=None, t_end=None):
+    """Samples that arrived in [t_begin, t_end + one period] (the poller is started long before the timed region:
+    the first nvidia-smi of a fresh box takes hundreds of milliseconds to initialise and stalls the GPU meanwhile)."""
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     time.sleep(0.15)
     self.proc.terminate()
     sm, mx, reasons = [], [], set()
-    for ln in self.lines:
+    lines = self.lines
+    if t_begin is not None:
+      inside = [(ts, ln) for ts, ln in lines if t_begin <= ts <= t_end + 0.12]
+      lines = inside if inside else lines[-2:]   # a region shorter than the polling period: the nearest samples
+    for ts, ln in lines:
       f = [x.strip() for x in ln.split(',')]
       if len(f) < 9:
         continue
@@ -152,7 +160,8 @@ def main():
                         '%d chains per GPU' % args.chains,
             'chains_per_gpu': args.chains, 'chains_total': args.chains * max(world, 1), 'dim': D,
             'max_tree_depth': MAX_DEPTH, 'parallelism': 'chains sharded, no data-path collective',
-            'l2': 'flushed (256 MiB write) before the timed launch; the K timed steps are ONE fused sample_chain launch',
+            'l2': 'flushed (256 MiB write) before every timed launch; the K timed steps are ONE fused sample_chain launch; '
+                  'the K-step region is measured 3 times and the median repetition is reported (timed_reps_ms)',
             'init': 'exact target draws; step size from %d untimed dual-averaging steps' % ADAPT_STEPS}
 
   if args.impl == 'reference':
@@ -210,47 +219,52 @@ def main():
     st, kr = nuts.one_step(st, kr, seed=step_seed)
     return st, kr, sd
 
+  sampler = ClockSampler(local_rank)   # polls during warm-up too; only the timed region's samples are reported
+  sampler.start()
   for _ in range(max(args.warmup, 3)):
     state, pkr, seed = one_transition(state, pkr, seed)
-  # warm-up of the fused driver itself (same code path as the timed launch: allocations, module load)
-  wres = tfp.mcmc.sample_chain(max(args.warmup, 3), state, kernel=nuts, previous_kernel_results=pkr, trace_fn=None,
-                               seed=20, return_final_kernel_results=True)
+  # warm-up of the fused driver itself (same code path and the same K as the timed launch: allocations, module load)
+  wres = tfp.mcmc.sample_chain(max(args.warmup, 3, args.steps), state, kernel=nuts, previous_kernel_results=pkr,
+                               trace_fn=None, seed=20, return_final_kernel_results=True)
   state, pkr = wres.all_states[-1].contiguous(), wres.final_kernel_results
   del wres
   torch.cuda.synchronize()
 
   # ---- timed region: K transitions of every chain as ONE sample_chain call (the fused driver: key schedule
-  # kernel + persistent transition kernel), L2 flushed before it, CUDA events on the launch stream
-  flush.fill_(1)
-  if world > 1:
-    dist.barrier()
-  torch.cuda.synchronize()
-  sampler = ClockSampler(local_rank)
-  sampler.start()
+  # kernel + persistent transition kernel), L2 flushed before it, CUDA events on the launch stream.  The region is
+  # measured 3 times (fresh seeds, L2 flushed each time) and the MEDIAN repetition is reported: a fresh box's first
+  # seconds are noisy (all three are listed in `timed_reps_ms`).
+  reps = []
+  t_begin = time.time()
   launches0 = ctx.launch_count()
-  tot = torch.zeros(B, dtype=torch.int64, device=dev)
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
-  res = tfp.mcmc.sample_chain(args.steps, state, kernel=nuts, previous_kernel_results=pkr, trace_fn=None, seed=19,
-                              experimental_leapfrog_total=tot, return_final_kernel_results=True)
-  e1.record()
-  torch.cuda.synchronize()
-  launches = ctx.launch_count() - launches0
-  clocks = sampler.stop()
-  if world > 1:
-    dist.barrier()
-  total_s = e0.elapsed_time(e1) / 1e3
-  n_grad = float(tot.sum().item())
-  tt = torch.tensor([total_s], device=dev, dtype=torch.float64)
-  ng = torch.tensor([n_grad], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dist.all_reduce(ng, op=dist.ReduceOp.SUM)
-  total_s = float(tt.item())
-  n_grad_all = float(ng.item())
+  for rep in range(3):
+    flush.fill_(1)
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    tot = torch.zeros(B, dtype=torch.int64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = tfp.mcmc.sample_chain(args.steps, state, kernel=nuts, previous_kernel_results=pkr, trace_fn=None,
+                                seed=19 + 1000 * rep, experimental_leapfrog_total=tot, return_final_kernel_results=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    ng = torch.tensor([float(tot.sum().item())], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      dist.all_reduce(ng, op=dist.ReduceOp.SUM)
+    reps.append((float(tt.item()), float(ng.item()), float(tot.sum().item())))
+    state = res.all_states[-1].contiguous()
+    pkr = res.final_kernel_results
+    del res
+  launches = (ctx.launch_count() - launches0) // 3
+  t_end = time.time()
+  clocks = sampler.stop(t_begin, t_end)
+  total_s, n_grad_all, n_grad = sorted(reps)[1]
   value = n_grad_all / total_s
-  state = res.all_states[-1].contiguous()
-  pkr = res.final_kernel_results
   step_ms = [1e3 * total_s]     # one launch covers the K steps
 
   # ---- the same K transitions as K separate one_step launches (what adaptation / TransitionKernel.one_step
@@ -379,6 +393,7 @@ def main():
                                'note': 'H2D initial state + ONE sample_chain(num_results=%d) + D2H of all states' % e2e_steps}},
           'roofline': roofline, 'cpu_baseline': cpu_baseline, 'step_size': eps,
           'leapfrogs_per_transition': n_grad / (B * args.steps),
+          'timed_reps_ms': [1e3 * r[0] for r in reps],
           'per_launch_run': {'value': fused_value, 'unit': UNIT,
                              'note': 'same K transitions as K one_step launches, L2 flushed between launches'},
           'min_ess': ess_info}
