@@ -305,7 +305,7 @@ def main():
     cnt_pinned.copy_(r.trace[0], non_blocking=True)
     torch.cuda.synchronize()
     e2e_grad += int(cnt_pinned.sum())
-    x_pinned.copy_(out_pinned)
+    x_pinned, out_pinned = out_pinned, x_pinned   # the step's host output is the next step's host input
   e2e_s = time.perf_counter() - t0
   ee = torch.tensor([float(e2e_grad), e2e_s], device=dev, dtype=torch.float64)
   if world > 1:
@@ -372,6 +372,7 @@ def main():
   achieved = flops / avg_launch_s / 1e12
   peak = 0.5 * pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+              'frac_of_3xtf32_peak': achieved / (peak / 3.0),   # FP32-accurate split: 3 tensor-core passes per flop
               'traffic': NCU_DRAM_BYTES_PER_TRANSITION * args.steps,
               'traffic_source': 'ncu --set full of this kernel (profiles/r01_tile_nuts_async_ncu_full_summary.csv): '
                                 'dram read+write bytes per transition of 16,384 chains, scaled to the K of this launch',
