@@ -126,6 +126,12 @@ int pb2_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, c
 int pb2_dense_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, float* d_logp,
                            float* d_grad);
 
+/* Same contract as pb2_logp_grad for a logistic-regression target (D <= 32 incl. the bias column), evaluated for
+ * all chains at once on the tcgen05 tensor cores: logits = Theta X~^T and grad = (y - sigmoid(logits)) X~ as two
+ * 3xTF32 contractions per 128-chain tile with the [128 x N] logits kept in TMEM (gym logistic_regression.py:88-103). */
+int pb2_logistic_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, float* d_logp,
+                              float* d_grad);
+
 /* ---- transitions / sample_chain -------------------------------------------------- */
 typedef struct {
   int kind;                 /* PB2_KERNEL_HMC | PB2_KERNEL_NUTS */

@@ -96,6 +96,7 @@ def load():
         'pb2_rng_randint': ([vp, c_u32p, ll, i32, i32, i32, vp], i32),
         'pb2_logp_grad': ([vp, vp, i32, vp, vp, vp], i32),
         'pb2_dense_logp_grad_tc': ([vp, vp, i32, vp, vp, vp], i32),
+        'pb2_logistic_logp_grad_tc': ([vp, vp, i32, vp, vp, vp], i32),
         'pb2_leapfrog': ([vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp], i32),
         'pb2_run': ([vp, vp, C.POINTER(ChainLayout), C.POINTER(RunCfg), c_u32p, c_u32p, vp, vp, vp, vp,
                      C.POINTER(DA), C.POINTER(Trace), vp], i32),

@@ -177,6 +177,7 @@ int pb2_target_destroy(pb2_target* t) {
   if (!t) return PB2_OK;
   cudaFree(t->d_a);
   cudaFree(t->d_b);
+  cudaFree(t->d_tc);
   delete t;
   return PB2_OK;
 }

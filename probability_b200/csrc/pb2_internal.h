@@ -36,6 +36,8 @@ struct pb2_target {
   float* d_a = nullptr;
   float* d_b = nullptr;
   float scalar = 0.f;
+  unsigned char* d_tc = nullptr;   // logistic: X~ pre-split into the tensor-core operand planes (pb2_logistic_tc.cu)
+  size_t tc_bytes = 0;
 };
 
 namespace pb2 {
@@ -66,6 +68,9 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
 // pb2_tile_nuts.cu (64-chain tiles: lock-step and asynchronous-lane NUTS)
 int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p);
+
+// pb2_logistic_tc.cu
+int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g);
 
 // pb2_misc.cu
 int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);

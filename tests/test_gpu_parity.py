@@ -660,3 +660,29 @@ def test_tile_kernels_chain_sharding_is_bit_identical(tfp, sampler):
   hi = run(x0[B // 2:], tfp.mcmc.ChainShard(B // 2, B))
   for f, a, b in zip(full, lo, hi):
     np.testing.assert_array_equal(f, np.concatenate([a, b], axis=1))
+
+
+@pytest.mark.parametrize('B,N', [(300, 1000), (128, 77)])
+def test_tensor_core_logistic_logp_grad_is_fp32_accurate(tfp, B, N):
+  """pb2_logistic_logp_grad_tc (two tcgen05 3xTF32 contractions around the sigmoid, logits kept in TMEM):
+  as close to float64 as the FP32 warp-per-chain kernel."""
+  from probability_b200 import _lib
+  X, y = otargets.synthetic_logistic_data(N, 24, seed=3)        # X includes the ones column
+  tg = tfp.targets.LogisticRegression(X[:, :-1], y)
+  o64 = otargets.LogisticRegression(X, y, dtype=np.float64)
+  th = (0.5 * np.random.default_rng(5).standard_normal((B, 25))).astype(np.float32)
+  ctx = _lib.Context.get(dev()); ctx.bind_stream()
+  tht = t(th)
+  lp = torch.empty(B, device=dev()); g = torch.empty(B, 25, device=dev())
+  _lib.check(ctx.lib.pb2_logistic_logp_grad_tc(ctx.handle, tg.handle(ctx), B, _lib.ptr(tht), _lib.ptr(lp), _lib.ptr(g)),
+             ctx.handle)
+  lp2 = torch.empty(B, device=dev()); g2 = torch.empty(B, 25, device=dev())
+  _lib.check(ctx.lib.pb2_logp_grad(ctx.handle, tg.handle(ctx), B, _lib.ptr(tht), _lib.ptr(lp2), _lib.ptr(g2)), ctx.handle)
+  lp64, g64 = o64.logp_grad(th.astype(np.float64))
+  scale = np.abs(g64).max(1, keepdims=True)
+  err_tc = np.max(np.abs(g.cpu().numpy() - g64) / scale)
+  err_fp = np.max(np.abs(g2.cpu().numpy() - g64) / scale)
+  assert err_tc < 3 * max(err_fp, 2e-6), (err_tc, err_fp)
+  elp_tc = np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64))
+  elp_fp = np.max(np.abs(lp2.cpu().numpy() - lp64) / np.abs(lp64))
+  assert elp_tc < 3 * max(elp_fp, 2e-6), (elp_tc, elp_fp)
