@@ -222,6 +222,10 @@ int pb2_rhat(pb2_ctx* ctx, const float* d_states, int N, int B, int D, int split
  * theta [B, D] -> d_packed [B, D+1] = (X~^T (y - sigmoid(X~ theta)) | sum_n log-lik). */
 int pb2_rowshard_logistic_grad(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
                                const float* d_theta, int B, float* d_packed);
+/* the same on the tcgen05 tensor cores (D <= 100): logits and gradient as two 3xTF32 contractions per 128-chain
+ * tile and 32-row chunk, row segments spread over the SMs, partial sums reduced in a fixed order */
+int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
+                                  const float* d_theta, int B, float* d_packed);
 /* grad = -theta + packed[:, :D]; logp = log N(theta; 0, I) + packed[:, D]
  * (inference_gym logistic_regression.py:88-103, bayesian_model.py:100-102). */
 int pb2_rowshard_logistic_finish(pb2_ctx* ctx, const float* d_packed, const float* d_theta, int B, int D,

@@ -23,108 +23,174 @@ using tile::tmem_wait_ld;
 
 namespace ltc {
 constexpr int kM = 128;        // chains per tile
-constexpr int kKD = 32;        // padded D (K of GEMM 1, N of GEMM 2)
-constexpr int kR = 64;         // rows of X~ per chunk (N of GEMM 1, K of GEMM 2)
-constexpr int kWorkers = 512;  // 16 worker warps: thread = (chain row, slice of 16 of the chunk's 64 rows of X~)
+constexpr int kWorkers = 512;  // 16 worker warps: thread = (chain row, slice = warp >> 2)
 constexpr int kThreads = kWorkers + 32;   // + warp 16: issues the contractions
 constexpr int kRing = 4;       // chunk operand buffers: GEMM 2 of c - 1 and c, GEMM 1 of c + 1, async copy of c + 2
-// TMEM columns: theta hi/lo | 2 x z chunk | 2 x r hi | 2 x r lo | 2 x g chunk
-constexpr int kColA1hi = 0, kColA1lo = 32, kColD1 = 64, kColA2hi = 192, kColA2lo = 320, kColD2 = 448;
-constexpr int kB1Plane = kR * kKD * 4;   // 8 KB: [n = 64 rows][k = 32 dims]
-constexpr int kB2Plane = kKD * kR * 4;   // 8 KB: [n = 32 dims][k = 64 rows]
-constexpr int kChunkBytes = 2 * kB1Plane + 2 * kB2Plane;   // hi/lo of both layouts = 32 KB
+
+// Shapes.  KD = padded D as the K of GEMM 1 (multiple of 8), ND = padded D as the N of GEMM 2 (multiple of 16),
+// R = rows of X~ per chunk (N of GEMM 1, K of GEMM 2).  TMEM columns: theta hi/lo | 2 x z chunk | 2 x r hi |
+// 2 x r lo | g chunk  =  2 KD + 6 R + ND <= 512.
+template <int KD_, int ND_, int R_>
+struct Shape {
+  static constexpr int KD = KD_, ND = ND_, R = R_;
+  static constexpr int kColA1hi = 0, kColA1lo = KD, kColD1 = 2 * KD, kColA2hi = 2 * KD + 2 * R,
+                       kColA2lo = 2 * KD + 4 * R, kColD2 = 2 * KD + 6 * R;
+  static_assert(kColD2 + ND <= 512, "TMEM budget");
+  static constexpr int kB1Plane = R * KD * 4;   // [n = R rows][k = KD dims]
+  static constexpr int kB2Plane = ND * R * 4;   // [n = ND dims][k = R rows]
+  static constexpr int kChunkBytes = 2 * kB1Plane + 2 * kB2Plane;   // hi/lo of both layouts
+  static constexpr int kTh = KD / 4;            // theta dims per worker thread
+  static constexpr int kG = ND / 4;             // gradient columns per worker thread
+  static constexpr int kZ = R / 4;              // logits per worker thread and chunk
+};
+using SmallD = Shape<32, 32, 64>;      // D <= 32 (C3: 1000 x 25): 480 columns, 32 KB per chunk
+using LargeD = Shape<104, 112, 32>;    // D <= 100 (C5: 1e6 x 100): 512 columns, 54 KB per chunk
 
 // byte offset of element (n, k) of a [NP x KP] K-major no-swizzle operand made of 8 x 16 B core matrices, K-chunk
 // major: LBO = (NP/8)*128 B between the two K core matrices of one MMA, SBO = 128 B between row groups
-template <int NP>
-__host__ __device__ inline int plane_offset(int n, int k) {
+__host__ __device__ inline int plane_offset(int NP, int n, int k) {
   return ((k >> 2) * (NP / 8) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 3) * 4;
 }
 
 __device__ __forceinline__ uint32_t tf32_round(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 
-// ---- one-time: X~ [N, D] -> per chunk the four planes (B1 hi, B1 lo, B2 hi, B2 lo) in the canonical layouts
-__global__ void logistic_tc_prepare_kernel(const float* __restrict__ X, int N, int D, unsigned char* __restrict__ out,
-                                           int nchunks) {
+// N consecutive TMEM columns of my lane <-> registers, N split greedily into the x16 / x8 / x4 / x2 / x1 shapes
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t a, uint32_t* v) {
+  if constexpr (N >= 16) { uint32_t t[16]; tmem_ld<16>(a, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = t[j];
+    if constexpr (N > 16) tmem_ld_n<N - 16>(a + 16, v + 16);
+  } else if constexpr (N >= 8) { uint32_t t[8]; tmem_ld<8>(a, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = t[j];
+    if constexpr (N > 8) tmem_ld_n<N - 8>(a + 8, v + 8);
+  } else if constexpr (N >= 4) { uint32_t t[4]; tmem_ld<4>(a, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = t[j];
+    if constexpr (N > 4) tmem_ld_n<N - 4>(a + 4, v + 4);
+  } else if constexpr (N >= 2) { uint32_t t[2]; tmem_ld<2>(a, t); v[0] = t[0]; v[1] = t[1];
+    if constexpr (N > 2) tmem_ld_n<N - 2>(a + 2, v + 2);
+  } else { uint32_t t[1]; tmem_ld<1>(a, t); v[0] = t[0]; }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t a, const uint32_t* v) {
+  if constexpr (N >= 16) { uint32_t t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = v[j];
+    tmem_st<16>(a, t);
+    if constexpr (N > 16) tmem_st_n<N - 16>(a + 16, v + 16);
+  } else if constexpr (N >= 8) { uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[j];
+    tmem_st<8>(a, t);
+    if constexpr (N > 8) tmem_st_n<N - 8>(a + 8, v + 8);
+  } else if constexpr (N >= 4) { uint32_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = v[j];
+    tmem_st<4>(a, t);
+    if constexpr (N > 4) tmem_st_n<N - 4>(a + 4, v + 4);
+  } else if constexpr (N >= 2) { uint32_t t[2] = {v[0], v[1]}; tmem_st<2>(a, t);
+    if constexpr (N > 2) tmem_st_n<N - 2>(a + 2, v + 2);
+  } else { uint32_t t[1] = {v[0]}; tmem_st<1>(a, t); }
+}
+
+// ---- one-time: X~ [N, ldx] -> per chunk the four planes (B1 hi, B1 lo, B2 hi, B2 lo) in the canonical layouts
+template <class S>
+__global__ void logistic_tc_prepare_kernel(const float* __restrict__ X, int N, int D, int ldx,
+                                           unsigned char* __restrict__ out) {
   const int chunk = blockIdx.x;
-  unsigned char* o = out + (size_t)chunk * kChunkBytes;
-  for (int i = threadIdx.x; i < kR * kKD; i += blockDim.x) {
-    const int r = i / kKD, d = i - r * kKD;   // row of the chunk, dim
-    const int n = chunk * kR + r;
-    const float v = (n < N && d < D) ? X[(size_t)n * D + d] : 0.f;
+  unsigned char* o = out + (size_t)chunk * S::kChunkBytes;
+  constexpr int DD = S::KD > S::ND ? S::KD : S::ND;
+  for (int i = threadIdx.x; i < S::R * DD; i += blockDim.x) {
+    const int r = i / DD, d = i - r * DD;   // row of the chunk, dim
+    const int n = chunk * S::R + r;
+    const float v = (n < N && d < D) ? X[(size_t)n * ldx + d] : 0.f;
     const uint32_t hi = tf32_round(v);
     const uint32_t lo = tf32_round(v - __uint_as_float(hi));
-    const int o1 = plane_offset<kR>(r, d);     // B1[n = r][k = d]
-    const int o2 = plane_offset<kKD>(d, r);    // B2[n = d][k = r]
-    *reinterpret_cast<uint32_t*>(o + o1) = hi;
-    *reinterpret_cast<uint32_t*>(o + kB1Plane + o1) = lo;
-    *reinterpret_cast<uint32_t*>(o + 2 * kB1Plane + o2) = hi;
-    *reinterpret_cast<uint32_t*>(o + 2 * kB1Plane + kB2Plane + o2) = lo;
+    if (d < S::KD) {
+      const int o1 = plane_offset(S::R, r, d);     // B1[n = r][k = d]
+      *reinterpret_cast<uint32_t*>(o + o1) = hi;
+      *reinterpret_cast<uint32_t*>(o + S::kB1Plane + o1) = lo;
+    }
+    if (d < S::ND) {
+      const int o2 = plane_offset(S::ND, d, r);    // B2[n = d][k = r]
+      *reinterpret_cast<uint32_t*>(o + 2 * S::kB1Plane + o2) = hi;
+      *reinterpret_cast<uint32_t*>(o + 2 * S::kB1Plane + S::kB2Plane + o2) = lo;
+    }
   }
 }
 
+template <class S>
 struct Smem {
-  unsigned long long g1_done[2], g2_done[2];   // mbarriers: the contraction into D1[b] / D2[b] has completed
+  unsigned long long g1_done[2], g2_done;   // mbarriers: the contraction into D1[b] / D2 has completed
   uint32_t tmem_base;
-  int quit;
-  float y[kRing][kR];
-  float valid[kRing][kR];
+  float y[kRing][S::R];
+  float valid[kRing][S::R];
   float red[4][kM];
 };
 
-// Software pipeline (per 128-chain tile, chunk c of 64 rows of X~):
-//   workers : start the async copy of chunk c+2's operands -> wait z(c) -> read it (D1[c%2] is free) -> signal A -> sigmoid /
-//             softplus of the 16 logits of my slice -> r hi/lo into A2[c%2] -> signal B
-//   issuer  : on A: GEMM 1 of chunk c+2 into D1[c%2];  on B: GEMM 2 of chunk c into D2[c%2]
+// Software pipeline (per 128-chain tile, chunk c of R rows of X~):
+//   workers : start the async copy of chunk c+2's operands -> wait z(c) -> read it (D1[c%2] is free) -> take the g
+//             chunk of c-1 out of D2 -> signal A -> sigmoid / softplus of my logits -> r hi/lo into A2[c%2] -> signal B
+//   issuer  : on A: GEMM 1 of chunk c+2 into D1[c%2];  on B: GEMM 2 of chunk c into D2
 // so both contractions run in the shadow of the workers' transcendental work.  UTCHMMA issue is back-pressured by
 // the tensor pipe, which is why it lives in a warp of its own.  Signals A / B are named barriers 2 / 3 on which the
 // workers only arrive.
+// kPartial = false: one CTA runs whole tiles over ALL rows and writes log-prob and gradient (prior included).
+// kPartial = true : CTA (tile = blockIdx.x, segment = blockIdx.y) covers `seg_chunks` chunks of the rows and writes its
+//                   partial sums part_g[segment][B][D], part_ll[segment][B] (row-sharded data: the caller reduces).
+template <class S, bool kPartial>
 __global__ void __launch_bounds__(kThreads, 1)
 logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const unsigned char* __restrict__ planes_g,
-                   const float* __restrict__ labels, int nchunks, float* __restrict__ out_lp, float* __restrict__ out_g) {
+                   const float* __restrict__ labels, int nchunks_total, int seg_chunks, float* __restrict__ out_lp,
+                   float* __restrict__ out_g) {
   extern __shared__ __align__(128) unsigned char ring[];   // kRing x (B1 hi, B1 lo, B2 hi, B2 lo)
-  __shared__ Smem sh;
+  __shared__ Smem<S> sh;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g1_done[b])));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g2_done[b])));
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g1_done[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g1_done[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g2_done)));
     asm volatile("fence.mbarrier_init.release.cluster;");
-    sh.quit = 0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = sh.tmem_base;
   const int ntiles = (B + kM - 1) / kM;
-  const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  // my tiles and my chunk range
+  const int tile0 = blockIdx.x, tile_step = kPartial ? ntiles : gridDim.x;   // kPartial: exactly one tile per CTA
+  const int cbeg = kPartial ? blockIdx.y * seg_chunks : 0;
+  const int cend = kPartial ? min(nchunks_total, cbeg + seg_chunks) : nchunks_total;
+  const int nchunks = max(0, cend - cbeg);
+  const int my_tiles = tile0 < ntiles ? (kPartial ? 1 : (ntiles - 1 - tile0) / tile_step + 1) : 0;
 
   if (warp == kWorkers / 32) {
     // ------------------------------------------------------------------ the issuing warp
-    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kR >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kKD >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::R >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::ND >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
     uint32_t leader;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
-    auto gemm1 = [&](int c) {   // z chunk = theta . X~chunk^T : 3 passes x 4 K-steps, M128 N64 K8
+    auto gemm1 = [&](int c) {   // z chunk = theta . X~chunk^T : 3 passes x KD/8 K-steps, M128 N=R K8
       if (!leader) return;
-      const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * kChunkBytes);
-      const uint64_t bhi = make_kmajor_desc(base, (kR / 8) * 128, 128);
-      const uint64_t blo = make_kmajor_desc(base + kB1Plane, (kR / 8) * 128, 128);
+      const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
+      const uint64_t bhi = make_kmajor_desc(base, (S::R / 8) * 128, 128);
+      const uint64_t blo = make_kmajor_desc(base + S::kB1Plane, (S::R / 8) * 128, 128);
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-        for (int j = 0; j < kKD / 8; ++j) {
-          const uint32_t a = tmem + (pass == 1 ? kColA1lo : kColA1hi) + 8 * j;
-          const uint64_t bd = (pass == 2 ? blo : bhi) + (uint64_t)(j * ((2u * (kR / 8) * 128u) >> 4));
+        for (int j = 0; j < S::KD / 8; ++j) {
+          const uint32_t a = tmem + (pass == 1 ? S::kColA1lo : S::kColA1hi) + 8 * j;
+          const uint64_t bd = (pass == 2 ? blo : bhi) + (uint64_t)(j * ((2u * (S::R / 8) * 128u) >> 4));
           const uint32_t acc = (pass == 0 && j == 0) ? 0u : 1u;
           asm volatile(
               "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + kColD1 + kR * (c & 1)),
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + S::kColD1 + S::R * (c & 1)),
               "r"(a), "l"(bd), "r"(idesc1), "r"(acc)
               : "memory");
         }
@@ -133,36 +199,36 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
                        smem_u32(&sh.g1_done[c & 1]))
                    : "memory");
     };
-    auto gemm2 = [&](int c) {   // g chunk = r . X~chunk : 3 passes x 8 K-steps, M128 N32 K8
+    auto gemm2 = [&](int c) {   // g chunk = r . X~chunk : 3 passes x R/8 K-steps, M128 N=ND K8
       if (!leader) return;
-      const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * kChunkBytes) + 2 * kB1Plane;
-      const uint64_t bhi = make_kmajor_desc(base, (kKD / 8) * 128, 128);
-      const uint64_t blo = make_kmajor_desc(base + kB2Plane, (kKD / 8) * 128, 128);
+      const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes) + 2 * S::kB1Plane;
+      const uint64_t bhi = make_kmajor_desc(base, (S::ND / 8) * 128, 128);
+      const uint64_t blo = make_kmajor_desc(base + S::kB2Plane, (S::ND / 8) * 128, 128);
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-        for (int j = 0; j < kR / 8; ++j) {
-          const uint32_t a = tmem + (pass == 1 ? kColA2lo : kColA2hi) + kR * (c & 1) + 8 * j;
-          const uint64_t bd = (pass == 2 ? blo : bhi) + (uint64_t)(j * ((2u * (kKD / 8) * 128u) >> 4));
+        for (int j = 0; j < S::R / 8; ++j) {
+          const uint32_t a = tmem + (pass == 1 ? S::kColA2lo : S::kColA2hi) + S::R * (c & 1) + 8 * j;
+          const uint64_t bd = (pass == 2 ? blo : bhi) + (uint64_t)(j * ((2u * (S::ND / 8) * 128u) >> 4));
           const uint32_t acc = (pass == 0 && j == 0) ? 0u : 1u;   // per-chunk product; chunks are summed in registers
           asm volatile(
               "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + kColD2 + kKD * (c & 1)),
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + S::kColD2),
               "r"(a), "l"(bd), "r"(idesc2), "r"(acc)
               : "memory");
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&sh.g2_done[c & 1]))
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sh.g2_done))
                    : "memory");
     };
     for (int tl = 0; tl < my_tiles; ++tl) {
+      if (nchunks == 0) break;
       asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // theta staged, chunks 0 and 1 copied
       asm volatile("tcgen05.fence::after_thread_sync;");
       gemm1(0);
       if (nchunks > 1) gemm1(1);
       for (int c = 0; c < nchunks; ++c) {
-        asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // D1[c%2] read, chunk c+2 copied
+        asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // D1[c%2] read, D2 read, chunk c+2 copied
         asm volatile("tcgen05.fence::after_thread_sync;");
         if (c + 2 < nchunks) gemm1(c + 2);
         asm volatile("bar.sync 3, %0;" ::"n"(kThreads) : "memory");   // A2[c%2] written
@@ -173,16 +239,16 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
   } else {
     // ------------------------------------------------------------------ the workers
     const int row = 32 * (warp & 3) + (tid & 31);   // chain of the tile = TMEM lane
-    const int slice = warp >> 2;                    // 16 of the chunk's 64 rows of X~ / 8 of the 32 dims
+    const int slice = warp >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    unsigned n1[2] = {0u, 0u}, n2[2] = {0u, 0u};    // completed waits per mbarrier (-> its phase parity)
-    auto stage = [&](int c) {   // chunk c's operand planes and labels -> ring slot c % kRing (cp.async, 16 B each)
-      const unsigned char* src = planes_g + (size_t)c * kChunkBytes;
-      const uint32_t dst = smem_u32(ring + (size_t)(c % kRing) * kChunkBytes);
-      for (int i = tid; i < kChunkBytes / 16; i += kWorkers)
+    unsigned n1[2] = {0u, 0u}, n2 = 0u;             // completed waits per mbarrier (-> its phase parity)
+    auto stage = [&](int c) {   // chunk cbeg + c's operand planes and labels -> ring slot c % kRing (cp.async, 16 B each)
+      const unsigned char* src = planes_g + (size_t)(cbeg + c) * S::kChunkBytes;
+      const uint32_t dst = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
+      for (int i = tid; i < S::kChunkBytes / 16; i += kWorkers)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 16 * (size_t)i) : "memory");
-      if (tid < kR) {
-        const int n = c * kR + tid;
+      if (tid < S::R) {
+        const int n = (cbeg + c) * S::R + tid;
         sh.y[c % kRing][tid] = n < N ? labels[n] : 0.f;
         sh.valid[c % kRing][tid] = n < N ? 1.f : 0.f;
       }
@@ -195,40 +261,42 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
       if (bar == 2) asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
       else asm volatile("bar.arrive 3, %0;" ::"n"(kThreads) : "memory");
     };
-    for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    for (int tl = 0; tl < my_tiles && nchunks > 0; ++tl) {
+      const int tile_i = tile0 + tl * tile_step;
       const int c0 = tile_i * kM + row;
       const bool live = c0 < B;
-      // ---- A1 = theta hi/lo: my 8 dims (slice) of my chain
-      float th[8];
+      // ---- A1 = theta hi/lo: my KD/4 dims (slice) of my chain
+      float th[S::kTh];
       float prior = 0.f;
       {
-        uint32_t hi[8], lo[8];
+        uint32_t hi[S::kTh], lo[S::kTh];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int d = 8 * slice + j;
+        for (int j = 0; j < S::kTh; ++j) {
+          const int d = S::kTh * slice + j;
           th[j] = (live && d < D) ? Theta[(size_t)c0 * D + d] : 0.f;
           if (d < D) prior += -0.5f * th[j] * th[j] - 0.9189385332046727f;
           hi[j] = tf32_round(th[j]);
           lo[j] = tf32_round(th[j] - __uint_as_float(hi[j]));
         }
-        tmem_st<8>(lane_addr + kColA1hi + 8 * slice, hi);
-        tmem_st<8>(lane_addr + kColA1lo + 8 * slice, lo);
+        tmem_st_n<S::kTh>(lane_addr + S::kColA1hi + S::kTh * slice, hi);
+        tmem_st_n<S::kTh>(lane_addr + S::kColA1lo + S::kTh * slice, lo);
       }
       stage(0);
       if (nchunks > 1) stage(1);
       signal(2);
       float ll = 0.f;   // my share of sum_n [y z - softplus z]
-      float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      auto take_g = [&](int c) {   // g chunk of chunk c: wait, add (FP32 adds keep the tensor core's sums short)
-        const int b = c & 1;
-        mbar_wait(smem_u32(&sh.g2_done[b]), n2[b] & 1u);
-        n2[b]++;
+      float gacc[S::kG];
+#pragma unroll
+      for (int j = 0; j < S::kG; ++j) gacc[j] = 0.f;
+      auto take_g = [&]() {   // the g chunk in D2: wait, add (FP32 adds keep the tensor core's sums short)
+        mbar_wait(smem_u32(&sh.g2_done), n2 & 1u);
+        n2++;
         asm volatile("tcgen05.fence::after_thread_sync;");
-        uint32_t gq[8];
-        tmem_ld<8>(lane_addr + kColD2 + kKD * b + 8 * slice, gq);
+        uint32_t gq[S::kG];
+        tmem_ld_n<S::kG>(lane_addr + S::kColD2 + S::kG * slice, gq);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gacc[j] += __uint_as_float(gq[j]);
+        for (int j = 0; j < S::kG; ++j) gacc[j] += __uint_as_float(gq[j]);
       };
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
@@ -237,18 +305,18 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
         mbar_wait(smem_u32(&sh.g1_done[b]), n1[b] & 1u);
         n1[b]++;
         asm volatile("tcgen05.fence::after_thread_sync;");
-        uint32_t zq[16];
-        tmem_ld<16>(lane_addr + kColD1 + kR * b + 16 * slice, zq);
+        uint32_t zq[S::kZ];
+        tmem_ld_n<S::kZ>(lane_addr + S::kColD1 + S::R * b + S::kZ * slice, zq);
         tmem_wait_ld();
-        // chunk c-1's contraction 2 is the last reader of A2[(c-1)%2] and the writer of D2[(c-1)%2]
-        if (c >= 1) take_g(c - 1);
+        // chunk c-1's contraction 2 is the last reader of A2[(c-1)%2] and the writer of D2
+        if (c >= 1) take_g();
         signal(2);
-        // ---- my 16 logits -> log-likelihood terms, r = y - sigmoid(z) -> A2[b] hi/lo
-        uint32_t hi[16], lo[16];
-        const float* yy = sh.y[c % kRing] + 16 * slice;
-        const float* vv = sh.valid[c % kRing] + 16 * slice;
+        // ---- my logits -> log-likelihood terms, r = y - sigmoid(z) -> A2[b] hi/lo
+        uint32_t hi[S::kZ], lo[S::kZ];
+        const float* yy = sh.y[c % kRing] + S::kZ * slice;
+        const float* vv = sh.valid[c % kRing] + S::kZ * slice;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < S::kZ; ++j) {
           const float z = __uint_as_float(zq[j]);
           // softplus(z) = max(z, 0) + log1p(exp(-|z|)); sigmoid(z) from the same exponential
           const float e = __expf(-fabsf(z));                 // same fast forms as the FP32 kernel (pb2_targets.cuh)
@@ -260,51 +328,135 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
           hi[j] = tf32_round(r);
           lo[j] = tf32_round(r - __uint_as_float(hi[j]));
         }
-        tmem_st<16>(lane_addr + kColA2hi + kR * b + 16 * slice, hi);
-        tmem_st<16>(lane_addr + kColA2lo + kR * b + 16 * slice, lo);
+        tmem_st_n<S::kZ>(lane_addr + S::kColA2hi + S::R * b + S::kZ * slice, hi);
+        tmem_st_n<S::kZ>(lane_addr + S::kColA2lo + S::R * b + S::kZ * slice, lo);
         signal(3);
       }
-      take_g(nchunks - 1);
-      // ---- g = sum of chunks - theta ; lp = prior + log-likelihood, summed over the 4 slices in a fixed order
-      if (live) {
+      take_g();
+      if constexpr (kPartial) {
+        // ---- partial sums of my row segment
+        float* pg = out_g + ((size_t)blockIdx.y * B + c0) * D;
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int d = 8 * slice + j;
-          if (d < D) out_g[(size_t)c0 * D + d] = gacc[j] - th[j];
+          for (int j = 0; j < S::kG; ++j) {
+            const int d = S::kG * slice + j;
+            if (d < D) pg[d] = gacc[j];
+          }
         }
+        sh.red[slice][row] = ll;
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+        if (live && slice == 0)
+          out_lp[(size_t)blockIdx.y * B + c0] = ((sh.red[0][row] + sh.red[1][row]) + sh.red[2][row]) + sh.red[3][row];
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+      } else {
+        // ---- g = sum of chunks - theta ; lp = prior + log-likelihood, summed over the 4 slices in a fixed order
+        // (gradient columns and theta dims are sliced alike only if kG == kTh: true for SmallD)
+        static_assert(kPartial || S::kG == S::kTh, "full mode needs matching theta / gradient slices");
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < S::kG; ++j) {
+            const int d = S::kG * slice + j;
+            if (d < D) out_g[(size_t)c0 * D + d] = gacc[j] - th[j];
+          }
+        }
+        sh.red[slice][row] = ll + prior;
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+        if (live && slice == 0) out_lp[c0] = ((sh.red[0][row] + sh.red[1][row]) + sh.red[2][row]) + sh.red[3][row];
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
       }
-      sh.red[slice][row] = ll + prior;
-      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
-      if (live && slice == 0) out_lp[c0] = ((sh.red[0][row] + sh.red[1][row]) + sh.red[2][row]) + sh.red[3][row];
-      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
+
+// packed[b][0..D) = sum over segments of part_g, packed[b][D] = sum of part_ll (fixed order: deterministic)
+__global__ void logistic_tc_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_ll, int S, int B,
+                                          int D, float* __restrict__ packed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * (D + 1)) return;
+  const int b = (int)(i / (D + 1)), d = (int)(i - (size_t)b * (D + 1));
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += d < D ? part_g[((size_t)s * B + b) * D + d] : part_ll[(size_t)s * B + b];
+  packed[i] = acc;
+}
 }  // namespace ltc
 
 int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g) {
   using namespace ltc;
+  using S = SmallD;
   const int D = tgt->dim, N = tgt->n_rows;
-  if (D > kKD) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_logistic_logp_grad_tc: D <= 32 only");
-  const int nchunks = (N + kR - 1) / kR;
-  const size_t need = (size_t)nchunks * kChunkBytes;
+  if (D > S::KD) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_logistic_logp_grad_tc: D <= 32 only");
+  const int nchunks = (N + S::R - 1) / S::R;
+  const size_t need = (size_t)nchunks * S::kChunkBytes;
   if (!tgt->d_tc) {   // the operand planes of this target, built once
     if (int rc = check_cuda(ctx, cudaMalloc(&tgt->d_tc, need), "cudaMalloc(logistic tc planes)")) return rc;
     tgt->tc_bytes = need;
-    logistic_tc_prepare_kernel<<<nchunks, 256, 0, ctx->stream>>>(tgt->d_a, N, D, tgt->d_tc, nchunks);
+    logistic_tc_prepare_kernel<S><<<nchunks, 256, 0, ctx->stream>>>(tgt->d_a, N, D, D, tgt->d_tc);
     ctx->launches += 1;
   }
-  const size_t smem = (size_t)kRing * kChunkBytes;
-  if (int rc = check_cuda(ctx, cudaFuncSetAttribute(logistic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+  const size_t smem = (size_t)kRing * S::kChunkBytes;
+  auto kern = logistic_tc_kernel<S, false>;
+  if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(logistic_tc)"))
     return rc;
   const int grid = std::min((B + kM - 1) / kM, ctx->num_sms);
-  logistic_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(d_x, B, D, N, tgt->d_tc, tgt->d_b, nchunks, d_lp, d_g);
+  kern<<<grid, kThreads, smem, ctx->stream>>>(d_x, B, D, N, tgt->d_tc, tgt->d_b, nchunks, nchunks, d_lp, d_g);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "logistic_tc_kernel");
+}
+
+// row-sharded data (C5): this rank's rows X [N, DP] (DP = padded row length), all chains; packed [B, D + 1]
+int launch_rowshard_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP, const float* d_theta, int B,
+                       float* d_packed) {
+  using namespace ltc;
+  using S = LargeD;
+  if (D > 100) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_rowshard_logistic_grad_tc: D <= 100 only");
+  const int nchunks = (N + S::R - 1) / S::R;
+  const size_t need = (size_t)std::max(nchunks, 1) * S::kChunkBytes;
+  if (ctx->rs_key != d_X || ctx->rs_N != N || ctx->rs_D != D) {   // operand planes of this shard, built once
+    if (ctx->rs_bytes < need) {
+      if (ctx->d_rs_planes) cudaFree(ctx->d_rs_planes);
+      ctx->d_rs_planes = nullptr;
+      ctx->rs_bytes = 0;
+      if (int rc = check_cuda(ctx, cudaMalloc(&ctx->d_rs_planes, need), "cudaMalloc(rowshard tc planes)")) return rc;
+      ctx->rs_bytes = need;
+    }
+    if (nchunks > 0) logistic_tc_prepare_kernel<S><<<nchunks, 256, 0, ctx->stream>>>(d_X, N, D, DP, ctx->d_rs_planes);
+    ctx->rs_key = d_X; ctx->rs_N = N; ctx->rs_D = D;
+    ctx->launches += 1;
+  }
+  const int ntiles = (B + kM - 1) / kM;
+  int nseg = std::max(1, ctx->num_sms / ntiles);
+  nseg = std::min(nseg, std::max(1, nchunks));
+  const int seg_chunks = (std::max(nchunks, 1) + nseg - 1) / nseg;
+  nseg = (std::max(nchunks, 1) + seg_chunks - 1) / seg_chunks;
+  const size_t pneed = sizeof(float) * ((size_t)nseg * B * D + (size_t)nseg * B);
+  if (pneed > ctx->sched_bytes) {
+    if (ctx->d_sched) cudaFree(ctx->d_sched);
+    ctx->d_sched = nullptr;
+    ctx->sched_bytes = 0;
+    if (int rc = check_cuda(ctx, cudaMalloc((void**)&ctx->d_sched, pneed), "cudaMalloc(rowshard partials)")) return rc;
+    ctx->sched_bytes = pneed;
+  }
+  float* part_g = reinterpret_cast<float*>(ctx->d_sched);
+  float* part_ll = part_g + (size_t)nseg * B * D;
+  if (int rc = check_cuda(ctx, cudaMemsetAsync(part_g, 0, pneed, ctx->stream), "memset(rowshard partials)")) return rc;
+  const size_t smem = (size_t)kRing * S::kChunkBytes;
+  auto kern = logistic_tc_kernel<S, true>;
+  if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(rowshard_tc)"))
+    return rc;
+  if (nchunks > 0) {
+    kern<<<dim3(ntiles, nseg), kThreads, smem, ctx->stream>>>(d_theta, B, D, N, ctx->d_rs_planes, d_y, nchunks, seg_chunks,
+                                                              part_ll, part_g);
+    ctx->launches += 1;
+  }
+  const size_t tot = (size_t)B * (D + 1);
+  logistic_tc_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part_g, part_ll, nseg, B, D, d_packed);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "rowshard_tc kernels");
 }
 
 }  // namespace pb2
@@ -316,4 +468,12 @@ extern "C" int pb2_logistic_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, in
   if (tgt->kind != PB2_TARGET_LOGISTIC)
     return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_logistic_logp_grad_tc: target must be a logistic regression");
   return pb2::launch_logistic_tc(ctx, const_cast<pb2_target*>(tgt), B, d_x, d_logp, d_grad);
+}
+
+extern "C" int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
+                                             const float* d_theta, int B, float* d_packed) {
+  if (!ctx || !d_X || !d_y || !d_theta || !d_packed || N < 0 || B < 1 || D < 1 || DP < D)
+    return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_rowshard_logistic_grad_tc: bad argument");
+  cudaSetDevice(ctx->device);
+  return pb2::launch_rowshard_tc(ctx, d_X, d_y, N, D, DP, d_theta, B, d_packed);
 }

@@ -85,3 +85,36 @@ def test_rowshard_hmc_matches_oracle_and_smem_path(tfp):
   states, acc = tfp.mcmc.sample_chain(5, st, kernel=k_big, trace_fn=lambda _, kr: kr.is_accepted, seed=3)
   assert states.shape == (5, B, d + 1) and acc.shape == (5, B)
   assert acc.float().mean() > 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,D,B', [(5000, 100, 300), (333, 37, 128), (40, 100, 130)])
+def test_rowshard_tensor_core_gradient_matches_fp32_and_float64(N, D, B):
+  """pb2_rowshard_logistic_grad_tc (tcgen05, 3xTF32, row segments over the SMs) == the FP32 kernel within rounding,
+  and as close to float64 as it."""
+  import probability_b200 as tfp
+  from probability_b200 import _lib
+  dev = torch.device('cuda', 0)
+  rng = np.random.default_rng(N + D)
+  X = rng.standard_normal((N, D - 1)).astype(np.float32)
+  y = (rng.random(N) < 0.5).astype(np.float32)
+  tg = tfp.targets.RowShardedLogisticRegression(X, y)
+  ctx = _lib.Context.get(dev); ctx.bind_stream()
+  Xd, yd = tg._device_data(dev)
+  th = (0.2 * rng.standard_normal((B, D))).astype(np.float32)
+  tht = torch.tensor(th, device=dev)
+  out = {}
+  for name in ('pb2_rowshard_logistic_grad', 'pb2_rowshard_logistic_grad_tc'):
+    packed = torch.empty(B, D + 1, device=dev)
+    _lib.check(getattr(ctx.lib, name)(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(tht), B,
+                                      _lib.ptr(packed)), ctx.handle)
+    out[name] = packed.cpu().numpy().astype(np.float64)
+  X64 = np.concatenate([X, np.ones((N, 1), np.float32)], 1).astype(np.float64)
+  z = th.astype(np.float64) @ X64.T
+  ll = (y[None] * z - np.logaddexp(0, z)).sum(1)
+  g = (y[None] - 1 / (1 + np.exp(-z))) @ X64
+  ref = np.concatenate([g, ll[:, None]], 1)
+  scale = np.abs(ref).max(1, keepdims=True)
+  e_fp = np.max(np.abs(out['pb2_rowshard_logistic_grad'] - ref) / scale)
+  e_tc = np.max(np.abs(out['pb2_rowshard_logistic_grad_tc'] - ref) / scale)
+  assert e_tc < 3 * max(e_fp, 2e-6), (e_tc, e_fp)
