@@ -223,8 +223,12 @@ int pb2_rhat(pb2_ctx* ctx, const float* d_states, int N, int B, int D, int split
 int pb2_rowshard_logistic_grad(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
                                const float* d_theta, int B, float* d_packed);
 /* the same on the tcgen05 tensor cores (D <= 100): logits and gradient as two 3xTF32 contractions per 128-chain
- * tile and 32-row chunk, row segments spread over the SMs, partial sums reduced in a fixed order */
-int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
+ * tile and 32-row chunk, row segments spread over the SMs, partial sums reduced in a fixed order.  The shard's rows
+ * are pre-split ONCE into tensor-core operand planes: the caller allocates pb2_rowshard_tc_planes_bytes(N) bytes,
+ * fills them with pb2_rowshard_tc_prepare and passes them to every gradient call. */
+long long pb2_rowshard_tc_planes_bytes(int N);
+int pb2_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, void* d_planes);
+int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const void* d_planes, const float* d_y, int N, int D,
                                   const float* d_theta, int B, float* d_packed);
 /* grad = -theta + packed[:, :D]; logp = log N(theta; 0, I) + packed[:, D]
  * (inference_gym logistic_regression.py:88-103, bayesian_model.py:100-102). */

@@ -106,7 +106,9 @@ def load():
         'pb2_ess': ([vp, vp, i32, i32, i32, f32, i32, i32, i32, vp], i32),
         'pb2_rhat': ([vp, vp, i32, i32, i32, i32, vp], i32),
         'pb2_rowshard_logistic_grad': ([vp, vp, vp, i32, i32, i32, vp, i32, vp], i32),
-        'pb2_rowshard_logistic_grad_tc': ([vp, vp, vp, i32, i32, i32, vp, i32, vp], i32),
+        'pb2_rowshard_tc_planes_bytes': ([i32], ll),
+        'pb2_rowshard_tc_prepare': ([vp, vp, i32, i32, i32, vp], i32),
+        'pb2_rowshard_logistic_grad_tc': ([vp, vp, vp, i32, i32, vp, i32, vp], i32),
         'pb2_rowshard_logistic_finish': ([vp, vp, vp, i32, i32, vp, vp], i32),
         'pb2_lockstep_leapfrog': ([vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp], i32),
     }

@@ -85,7 +85,6 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_queue);
   cudaFree(ctx->d_partial);
-  cudaFree(ctx->d_rs_planes);
   cudaFree(ctx->d_ckpt);
   cudaFree(ctx->d_sched);
   cudaFree(ctx->d_step_keys);

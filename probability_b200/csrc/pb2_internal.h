@@ -26,10 +26,6 @@ struct pb2_ctx {
   float* d_step_seq = nullptr;     // per-transition scalar step sizes (dual averaging)
   size_t step_seq_bytes = 0;
   float* d_partial = nullptr;      // [2] dual-averaging partial
-  unsigned char* d_rs_planes = nullptr;   // row-sharded logistic: this shard's X~ as tensor-core operand planes
-  const float* rs_key = nullptr;          //   ... built for this (X pointer, N, D)
-  int rs_N = 0, rs_D = 0;
-  size_t rs_bytes = 0;
 };
 
 struct pb2_target {
@@ -75,8 +71,10 @@ int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p);
 
 // pb2_logistic_tc.cu
 int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g);
-int launch_rowshard_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP, const float* d_theta, int B,
-                       float* d_packed);
+size_t rowshard_tc_planes_bytes(int N);
+int launch_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, unsigned char* d_planes);
+int launch_rowshard_tc(pb2_ctx* ctx, const unsigned char* d_planes, const float* d_y, int N, int D, const float* d_theta,
+                       int B, float* d_packed);
 
 // pb2_misc.cu
 int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);

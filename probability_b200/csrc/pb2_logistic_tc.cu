@@ -407,26 +407,31 @@ int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, f
   return check_cuda(ctx, cudaGetLastError(), "logistic_tc_kernel");
 }
 
-// row-sharded data (C5): this rank's rows X [N, DP] (DP = padded row length), all chains; packed [B, D + 1]
-int launch_rowshard_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP, const float* d_theta, int B,
-                       float* d_packed) {
+// row-sharded data (C5): this rank's rows as operand planes (built once by launch_rowshard_tc_prepare into a
+// caller-owned buffer), all chains; packed [B, D + 1]
+size_t rowshard_tc_planes_bytes(int N) {
+  using S = ltc::LargeD;
+  return (size_t)std::max((N + S::R - 1) / S::R, 1) * S::kChunkBytes;
+}
+
+int launch_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, unsigned char* d_planes) {
+  using namespace ltc;
+  using S = LargeD;
+  if (D > 100) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_rowshard_tc_prepare: D <= 100 only");
+  const int nchunks = (N + S::R - 1) / S::R;
+  if (nchunks > 0) {
+    logistic_tc_prepare_kernel<S><<<nchunks, 256, 0, ctx->stream>>>(d_X, N, D, DP, d_planes);
+    ctx->launches += 1;
+  }
+  return check_cuda(ctx, cudaGetLastError(), "logistic_tc_prepare_kernel");
+}
+
+int launch_rowshard_tc(pb2_ctx* ctx, const unsigned char* d_planes, const float* d_y, int N, int D, const float* d_theta,
+                       int B, float* d_packed) {
   using namespace ltc;
   using S = LargeD;
   if (D > 100) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_rowshard_logistic_grad_tc: D <= 100 only");
   const int nchunks = (N + S::R - 1) / S::R;
-  const size_t need = (size_t)std::max(nchunks, 1) * S::kChunkBytes;
-  if (ctx->rs_key != d_X || ctx->rs_N != N || ctx->rs_D != D) {   // operand planes of this shard, built once
-    if (ctx->rs_bytes < need) {
-      if (ctx->d_rs_planes) cudaFree(ctx->d_rs_planes);
-      ctx->d_rs_planes = nullptr;
-      ctx->rs_bytes = 0;
-      if (int rc = check_cuda(ctx, cudaMalloc(&ctx->d_rs_planes, need), "cudaMalloc(rowshard tc planes)")) return rc;
-      ctx->rs_bytes = need;
-    }
-    if (nchunks > 0) logistic_tc_prepare_kernel<S><<<nchunks, 256, 0, ctx->stream>>>(d_X, N, D, DP, ctx->d_rs_planes);
-    ctx->rs_key = d_X; ctx->rs_N = N; ctx->rs_D = D;
-    ctx->launches += 1;
-  }
   const int ntiles = (B + kM - 1) / kM;
   int nseg = std::max(1, ctx->num_sms / ntiles);
   nseg = std::min(nseg, std::max(1, nchunks));
@@ -449,8 +454,8 @@ int launch_rowshard_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, 
                           "cudaFuncSetAttribute(rowshard_tc)"))
     return rc;
   if (nchunks > 0) {
-    kern<<<dim3(ntiles, nseg), kThreads, smem, ctx->stream>>>(d_theta, B, D, N, ctx->d_rs_planes, d_y, nchunks, seg_chunks,
-                                                              part_ll, part_g);
+    kern<<<dim3(ntiles, nseg), kThreads, smem, ctx->stream>>>(d_theta, B, D, N, d_planes, d_y, nchunks, seg_chunks, part_ll,
+                                                              part_g);
     ctx->launches += 1;
   }
   const size_t tot = (size_t)B * (D + 1);
@@ -470,10 +475,19 @@ extern "C" int pb2_logistic_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, in
   return pb2::launch_logistic_tc(ctx, const_cast<pb2_target*>(tgt), B, d_x, d_logp, d_grad);
 }
 
-extern "C" int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const float* d_X, const float* d_y, int N, int D, int DP,
+extern "C" long long pb2_rowshard_tc_planes_bytes(int N) { return N < 0 ? -1 : (long long)pb2::rowshard_tc_planes_bytes(N); }
+
+extern "C" int pb2_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, void* d_planes) {
+  if (!ctx || !d_X || !d_planes || N < 0 || D < 1 || DP < D)
+    return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_rowshard_tc_prepare: bad argument");
+  cudaSetDevice(ctx->device);
+  return pb2::launch_rowshard_tc_prepare(ctx, d_X, N, D, DP, static_cast<unsigned char*>(d_planes));
+}
+
+extern "C" int pb2_rowshard_logistic_grad_tc(pb2_ctx* ctx, const void* d_planes, const float* d_y, int N, int D,
                                              const float* d_theta, int B, float* d_packed) {
-  if (!ctx || !d_X || !d_y || !d_theta || !d_packed || N < 0 || B < 1 || D < 1 || DP < D)
+  if (!ctx || !d_planes || !d_y || !d_theta || !d_packed || N < 0 || B < 1 || D < 1)
     return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_rowshard_logistic_grad_tc: bad argument");
   cudaSetDevice(ctx->device);
-  return pb2::launch_rowshard_tc(ctx, d_X, d_y, N, D, DP, d_theta, B, d_packed);
+  return pb2::launch_rowshard_tc(ctx, static_cast<const unsigned char*>(d_planes), d_y, N, D, d_theta, B, d_packed);
 }

@@ -159,7 +159,8 @@ class RowShardedLogisticRegression(Target):
   (replicated, identical RNG: no fold_in_axis_index, like an unsharded state part in
   hmc_test.py:1246-1272) and `features_local`/`labels_local`, its slice of the data.
 
-  One gradient evaluation = local pass over the rows for ALL chains (pb2_rowshard_logistic_grad)
+  One gradient evaluation = local pass over the rows for ALL chains (pb2_rowshard_logistic_grad_tc: two tcgen05
+  contractions around the sigmoid; pb2_rowshard_logistic_grad, FP32, below 128 chains)
   + ONE all-reduce of the packed `[B, D+1]` (gradient | log-lik) buffer over NVLink (the psum of
   distribute_lib.py:179-186 and its pbroadcast VJP :228-242) + prior (pb2_rowshard_logistic_finish).
   Transitions with this target run lock-step over chains (one kernel sequence per leapfrog)."""
@@ -184,6 +185,7 @@ class RowShardedLogisticRegression(Target):
     self._Xp = Xp
     self._y = y
     self.process_group = process_group
+    self.use_tensor_cores = True    # False: always the FP32 kernel (A/B)
     self._dev = {}
 
   def _device_data(self, device):
@@ -195,6 +197,19 @@ class RowShardedLogisticRegression(Target):
 
   def handle(self, ctx):
     raise _lib.Pb2Error('RowShardedLogisticRegression runs the lock-step path; it has no per-chain kernel')
+
+  def _tc_planes(self, ctx, device):
+    """This shard's rows pre-split into the tensor-core operand planes (built once per device)."""
+    import torch
+    key = ('tc', device.index)
+    if key not in self._dev:
+      X, _ = self._device_data(device)
+      nbytes = int(ctx.lib.pb2_rowshard_tc_planes_bytes(self.n_rows))
+      planes = torch.empty(nbytes, dtype=torch.uint8, device=device)
+      _lib.check(ctx.lib.pb2_rowshard_tc_prepare(ctx.handle, _lib.ptr(X), self.n_rows, self.dim, self.padded_dim,
+                                                 _lib.ptr(planes)), ctx.handle)
+      self._dev[key] = planes
+    return self._dev[key]
 
   def _world(self):
     import torch.distributed as dist
@@ -212,8 +227,14 @@ class RowShardedLogisticRegression(Target):
     X, y = self._device_data(x.device)
     B = x.shape[0]
     packed = torch.empty(B, self.dim + 1, dtype=torch.float32, device=x.device)
-    _lib.check(ctx.lib.pb2_rowshard_logistic_grad(ctx.handle, _lib.ptr(X), _lib.ptr(y), self.n_rows, self.dim,
-                                                  self.padded_dim, _lib.ptr(x), B, _lib.ptr(packed)), ctx.handle)
+    # tcgen05 contractions for a tile's worth of chains or more; the FP32 thread-per-chain kernel for small batches
+    if B >= 128 and self.use_tensor_cores:
+      planes = self._tc_planes(ctx, x.device)
+      _lib.check(ctx.lib.pb2_rowshard_logistic_grad_tc(ctx.handle, _lib.ptr(planes), _lib.ptr(y), self.n_rows, self.dim,
+                                                       _lib.ptr(x), B, _lib.ptr(packed)), ctx.handle)
+    else:
+      _lib.check(ctx.lib.pb2_rowshard_logistic_grad(ctx.handle, _lib.ptr(X), _lib.ptr(y), self.n_rows, self.dim,
+                                                    self.padded_dim, _lib.ptr(x), B, _lib.ptr(packed)), ctx.handle)
     dist = self._world()
     if dist is not None:
       dist.all_reduce(packed, group=self.process_group)     # per-leapfrog gradient all-reduce (NCCL/NVLink)

@@ -18,14 +18,17 @@ Xd, yd = tg._device_data(dev)
 th = torch.zeros(B, D, device=dev) + 0.01 * torch.randn(B, D, device=dev)
 packed = torch.empty(B, D + 1, device=dev)
 import ctypes
-for name, fn in (('fp32 thread-per-chain', ctx.lib.pb2_rowshard_logistic_grad), ('tcgen05', ctx.lib.pb2_rowshard_logistic_grad_tc)):
+planes = tg._tc_planes(ctx, dev)
+fp32 = lambda: ctx.lib.pb2_rowshard_logistic_grad(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(th), B, _lib.ptr(packed))
+tc = lambda: ctx.lib.pb2_rowshard_logistic_grad_tc(ctx.handle, _lib.ptr(planes), _lib.ptr(yd), N, D, _lib.ptr(th), B, _lib.ptr(packed))
+for name, fn in (('fp32 thread-per-chain', fp32), ('tcgen05', tc)):
  for _ in range(2):
-  _lib.check(fn(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(th), B, _lib.ptr(packed)), ctx.handle)
+  _lib.check(fn(), ctx.handle)
  torch.cuda.synchronize()
  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
  e0.record()
  for _ in range(5):
-  fn(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(th), B, _lib.ptr(packed))
+  fn()
  e1.record(); torch.cuda.synchronize()
  ms = e0.elapsed_time(e1) / 5
  flop = 4.0 * N * D * B

@@ -104,11 +104,14 @@ def test_rowshard_tensor_core_gradient_matches_fp32_and_float64(N, D, B):
   th = (0.2 * rng.standard_normal((B, D))).astype(np.float32)
   tht = torch.tensor(th, device=dev)
   out = {}
-  for name in ('pb2_rowshard_logistic_grad', 'pb2_rowshard_logistic_grad_tc'):
-    packed = torch.empty(B, D + 1, device=dev)
-    _lib.check(getattr(ctx.lib, name)(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(tht), B,
-                                      _lib.ptr(packed)), ctx.handle)
-    out[name] = packed.cpu().numpy().astype(np.float64)
+  packed = torch.empty(B, D + 1, device=dev)
+  _lib.check(ctx.lib.pb2_rowshard_logistic_grad(ctx.handle, _lib.ptr(Xd), _lib.ptr(yd), N, D, tg.padded_dim, _lib.ptr(tht),
+                                                B, _lib.ptr(packed)), ctx.handle)
+  out['pb2_rowshard_logistic_grad'] = packed.cpu().numpy().astype(np.float64)
+  packed = torch.empty(B, D + 1, device=dev)
+  _lib.check(ctx.lib.pb2_rowshard_logistic_grad_tc(ctx.handle, _lib.ptr(tg._tc_planes(ctx, dev)), _lib.ptr(yd), N, D,
+                                                   _lib.ptr(tht), B, _lib.ptr(packed)), ctx.handle)
+  out['pb2_rowshard_logistic_grad_tc'] = packed.cpu().numpy().astype(np.float64)
   X64 = np.concatenate([X, np.ones((N, 1), np.float32)], 1).astype(np.float64)
   z = th.astype(np.float64) @ X64.T
   ll = (y[None] * z - np.logaddexp(0, z)).sum(1)
