@@ -54,32 +54,34 @@ def main():
     np.testing.assert_allclose(a.cpu().numpy(), b[:, rank * B:(rank + 1) * B].cpu().numpy(), rtol=1e-5, atol=1e-6)
 
   # ---------------- (b) row sharding with per-leapfrog gradient all-reduce
-  n, d, Bc = 4000, 39, 96
-  X, y = tfp.targets.synthetic_logistic_data(n, d, seed=1)
-  per = n // world
-  lo, hi = rank * per, (n if rank == world - 1 else (rank + 1) * per)
-  t_shard = tfp.targets.RowShardedLogisticRegression(X[lo:hi], y[lo:hi])
-  t_full = tfp.targets.RowShardedLogisticRegression(X, y)
-  t_full._world = lambda: None                # all rows local: no collective
-  st = torch.tensor((0.1 * np.random.default_rng(2).standard_normal((Bc, d + 1))).astype(np.float32), device=dev)
-  outs = []
-  for t in (t_shard, t_full):
-    k = tfp.mcmc.HamiltonianMonteCarlo(t, step_size=0.01, num_leapfrog_steps=4)
-    outs.append(tfp.mcmc.sample_chain(4, st, kernel=k, seed=5,
-                                      trace_fn=lambda _, kr: (kr.is_accepted, kr.log_accept_ratio)))
-  sh, fu = outs
-  np.testing.assert_allclose(sh.trace[1].cpu().numpy(), fu.trace[1].cpu().numpy(), rtol=5e-3, atol=5e-3)
-  agree = (sh.trace[0] == fu.trace[0]).float().mean().item()
-  assert agree > 0.97, agree
-  acc = sh.trace[0].to(torch.int32).contiguous()
-  g = [torch.zeros_like(acc) for _ in range(world)]
-  dist.all_gather(g, acc)
-  for a in g:                                  # replicas take bit-identical decisions
-    assert torch.equal(a, acc)
-  s = [torch.zeros_like(sh.all_states) for _ in range(world)]
-  dist.all_gather(s, sh.all_states.contiguous())
-  for a in s:
-    assert torch.equal(a, sh.all_states)
+  # (96 chains: FP32 thread-per-chain gradient; 256 chains: the tcgen05 gradient)
+  n, d = 4000, 39
+  for Bc in (96, 256):
+    X, y = tfp.targets.synthetic_logistic_data(n, d, seed=1)
+    per = n // world
+    lo, hi = rank * per, (n if rank == world - 1 else (rank + 1) * per)
+    t_shard = tfp.targets.RowShardedLogisticRegression(X[lo:hi], y[lo:hi])
+    t_full = tfp.targets.RowShardedLogisticRegression(X, y)
+    t_full._world = lambda: None                # all rows local: no collective
+    st = torch.tensor((0.1 * np.random.default_rng(2).standard_normal((Bc, d + 1))).astype(np.float32), device=dev)
+    outs = []
+    for t in (t_shard, t_full):
+      k = tfp.mcmc.HamiltonianMonteCarlo(t, step_size=0.01, num_leapfrog_steps=4)
+      outs.append(tfp.mcmc.sample_chain(4, st, kernel=k, seed=5,
+                                        trace_fn=lambda _, kr: (kr.is_accepted, kr.log_accept_ratio)))
+    sh, fu = outs
+    np.testing.assert_allclose(sh.trace[1].cpu().numpy(), fu.trace[1].cpu().numpy(), rtol=5e-3, atol=5e-3)
+    agree = (sh.trace[0] == fu.trace[0]).float().mean().item()
+    assert agree > 0.97, agree
+    acc = sh.trace[0].to(torch.int32).contiguous()
+    g = [torch.zeros_like(acc) for _ in range(world)]
+    dist.all_gather(g, acc)
+    for a in g:                                  # replicas take bit-identical decisions
+      assert torch.equal(a, acc)
+    s = [torch.zeros_like(sh.all_states) for _ in range(world)]
+    dist.all_gather(s, sh.all_states.contiguous())
+    for a in s:
+      assert torch.equal(a, sh.all_states)
   dist.barrier()
   if rank == 0:
     print('MULTIGPU OK world=%d' % world, flush=True)
