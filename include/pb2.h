@@ -9,6 +9,9 @@
  *                        normal, uniform) over jax.random
  *                        (internal/backend/numpy/random_generators.py:151-158,278-302)
  *   pb2_logp_grad        mcmc/internal/util.py:286-308 maybe_call_fn_and_grads
+ *   pb2_dense_/pb2_logistic_logp_grad_tc   the same, all chains at once on the tcgen05 tensor cores
+ *   pb2_rowshard_*       target_log_prob_fn + gradient of a logistic regression whose rows are sharded over ranks
+ *                        (psum in the target: internal/distribute_lib.py:147-162,179-242)
  *   pb2_leapfrog         mcmc/internal/leapfrog_integrator.py:222-316 SimpleLeapfrogIntegrator.__call__
  *   pb2_run (HMC)        mcmc/hmc.py:501-529,661-729 + mcmc/metropolis_hastings.py:160-254
  *   pb2_run (NUTS)       mcmc/nuts.py:321-445 NoUTurnSampler.one_step
