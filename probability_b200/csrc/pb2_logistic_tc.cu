@@ -42,6 +42,9 @@ struct Shape {
   static constexpr int kTh = KD / 4;            // theta dims per worker thread
   static constexpr int kG = ND / 4;             // gradient columns per worker thread
   static constexpr int kZ = R / 4;              // logits per worker thread and chunk
+  // the tensor core's accumulator truncates: it only sums kGroup chunks (128 rows) before the workers take the
+  // partial gradient out of D2 and add it in FP32 registers
+  static constexpr int kGroup = 128 / R;
 };
 using SmallD = Shape<32, 32, 64>;      // D <= 32 (C3: 1000 x 25): 480 columns, 32 KB per chunk
 using LargeD = Shape<104, 112, 32>;    // D <= 100 (C5: 1e6 x 100): 512 columns, 54 KB per chunk
@@ -210,7 +213,7 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
         for (int j = 0; j < S::R / 8; ++j) {
           const uint32_t a = tmem + (pass == 1 ? S::kColA2lo : S::kColA2hi) + S::R * (c & 1) + 8 * j;
           const uint64_t bd = (pass == 2 ? blo : bhi) + (uint64_t)(j * ((2u * (S::ND / 8) * 128u) >> 4));
-          const uint32_t acc = (pass == 0 && j == 0) ? 0u : 1u;   // per-chunk product; chunks are summed in registers
+          const uint32_t acc = (c % S::kGroup == 0 && pass == 0 && j == 0) ? 0u : 1u;   // D2 sums kGroup chunks
           asm volatile(
               "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + S::kColD2),
@@ -288,9 +291,10 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
       float gacc[S::kG];
 #pragma unroll
       for (int j = 0; j < S::kG; ++j) gacc[j] = 0.f;
-      auto take_g = [&]() {   // the g chunk in D2: wait, add (FP32 adds keep the tensor core's sums short)
-        mbar_wait(smem_u32(&sh.g2_done), n2 & 1u);
+      auto take_g = [&](bool read) {   // contraction 2 of the previous chunk: wait; at the end of a group of chunks
+        mbar_wait(smem_u32(&sh.g2_done), n2 & 1u);   // take the partial gradient out of D2 and add it in FP32
         n2++;
+        if (!read) return;
         asm volatile("tcgen05.fence::after_thread_sync;");
         uint32_t gq[S::kG];
         tmem_ld_n<S::kG>(lane_addr + S::kColD2 + S::kG * slice, gq);
@@ -309,7 +313,7 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
         tmem_ld_n<S::kZ>(lane_addr + S::kColD1 + S::R * b + S::kZ * slice, zq);
         tmem_wait_ld();
         // chunk c-1's contraction 2 is the last reader of A2[(c-1)%2] and the writer of D2
-        if (c >= 1) take_g();
+        if (c >= 1) take_g(c % S::kGroup == 0);
         signal(2);
         // ---- my logits -> log-likelihood terms, r = y - sigmoid(z) -> A2[b] hi/lo
         uint32_t hi[S::kZ], lo[S::kZ];
@@ -332,7 +336,7 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
         tmem_st_n<S::kZ>(lane_addr + S::kColA2lo + S::R * b + S::kZ * slice, lo);
         signal(3);
       }
-      take_g();
+      take_g(true);
       if constexpr (kPartial) {
         // ---- partial sums of my row segment
         float* pg = out_g + ((size_t)blockIdx.y * B + c0) * D;
