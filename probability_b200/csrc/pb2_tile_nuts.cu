@@ -1,8 +1,10 @@
 // 64-chain TILE NUTS kernels for the dense-Gaussian target (tcgen05 path, pb2_tile64.cuh):
 //   tile_nuts_kernel       : NoUTurnSampler.one_step (tfp/mcmc/nuts.py:321-946) for a tile run in LOCK-STEP, i.e.
 //                            literally the reference's batched algorithm (shared doubling / leaf counters,
-//                            per-chain masks) -- used for single transitions and during step-size adaptation;
-//   tile_nuts_async_kernel : fused multi-transition runs; every lane at its own position of its own tree.
+//                            per-chain masks) -- max_tree_depth <= 5, or dense_variant 3 (the bit-exact partner of
+//                            the asynchronous kernel in the tests);
+//   tile_nuts_async_kernel : every lane at its own position of its own tree and transition -- all other launches
+//                            (single transitions, adaptation steps and fused multi-transition runs).
 // Both call the same nuts_leaf(), so a chain's arithmetic is the same instruction sequence in both and the
 // results are bit-identical (tests/test_gpu_parity.py).
 #include <algorithm>
@@ -468,11 +470,11 @@ struct AsyncQueue {
   int* t_next;                 // [B] next transition of each chain
   int cap;                     // >= B + lanes: live tickets (waiting lanes + queued chains) never share a slot
 };
-enum { kQHead = 0, kQTail = 1, kQDone = 2 };
+enum { kQHead = 0, kQTail = 1 };
 
 __global__ void tile_async_init_kernel(AsyncQueue aq, int B, int t0) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) { aq.ctl[kQHead] = 0ull; aq.ctl[kQTail] = (unsigned long long)B; aq.ctl[kQDone] = 0ull; }
+  if (c == 0) { aq.ctl[kQHead] = 0ull; aq.ctl[kQTail] = (unsigned long long)B; }
   if (c < aq.cap) aq.q[c] = c < B ? c : -1;
   if (c < B) aq.t_next[c] = t0;
 }
