@@ -194,7 +194,9 @@ struct LogisticT {
   static_assert(E == 1 && !Grp::kIsBlock && DT <= 32, "logistic runs warp-per-chain, theta on lanes");
   using Params = LogisticParams;
   static constexpr bool kCkptInSmem = true;
-  static constexpr int RS = DT | 1;  // odd row stride: conflict-free when lanes walk rows
+  // row stride in floats: a multiple of 4 whose quarter is odd (25 -> 28), so that lanes walking rows read a row as
+  // 128-bit loads without bank conflicts (stride = 4 * odd words permutes the 8 x 16 B groups of a quarter-warp)
+  static constexpr int RS = (((DT + 3) / 4) | 1) * 4;
   const float* sX;
   const float* sy;
   int N, D;
@@ -215,31 +217,43 @@ struct LogisticT {
     D = p.D;
   }
   __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
-    float th[DT];
+    float th[RS];
 #pragma unroll
-    for (int d = 0; d < DT; ++d) th[d] = __shfl_sync(0xffffffffu, x[0], d);  // lanes >= D hold 0
-    float acc[32];
+    for (int d = 0; d < RS; ++d) th[d] = d < 32 ? __shfl_sync(0xffffffffu, x[0], d & 31) : 0.f;  // lanes >= D hold 0
+    // Both contractions of a row run on packed FP32 FMAs (FFMA2: two lanes of a register pair per instruction): the
+    // logit is accumulated as (even dims, odd dims) partial sums, the gradient as pairs of adjacent dims.
+    constexpr int kPairs = RS / 2;   // the padding columns of a row are zero
+    static_assert(kPairs <= 18, "D <= 32");
+    float2 acc2[18];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    for (int q = 0; q < 18; ++q) acc2[q] = make_float2(0.f, 0.f);
     float ll = 0.f;
     for (int n = grp.lane; n < N; n += 32) {
-      const float* row = sX + n * RS;
-      float xr[DT];
-      float z = 0.f;
+      const float4* row = reinterpret_cast<const float4*>(sX + n * RS);
+      float xr[RS];
 #pragma unroll
-      for (int d = 0; d < DT; ++d) {
-        xr[d] = row[d];
-        z = fmaf(xr[d], th[d], z);
+      for (int q = 0; q < RS / 4; ++q) {
+        const float4 v = row[q];
+        xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
       }
+      float2 z2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < kPairs; ++q)
+        z2 = __ffma2_rn(make_float2(xr[2 * q], xr[2 * q + 1]), make_float2(th[2 * q], th[2 * q + 1]), z2);
+      const float z = z2.x + z2.y;
       const float yn = sy[n];
       const float e = __expf(-fabsf(z));
       const float r = __fdividef(1.0f, 1.0f + e);
       const float sg = z >= 0.f ? r : e * r;
       ll += yn * z - (__logf(1.0f + e) + fmaxf(z, 0.f));
       const float w = yn - sg;
+      const float2 w2 = make_float2(w, w);
 #pragma unroll
-      for (int d = 0; d < DT; ++d) acc[d] = fmaf(xr[d], w, acc[d]);
+      for (int q = 0; q < kPairs; ++q) acc2[q] = __ffma2_rn(make_float2(xr[2 * q], xr[2 * q + 1]), w2, acc2[q]);
     }
+    float acc[32];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { acc[2 * q] = acc2[q].x; acc[2 * q + 1] = acc2[q].y; }
     // transpose-reduce: 31 shuffles leave the total of index l on lane l
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
