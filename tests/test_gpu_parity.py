@@ -686,3 +686,52 @@ def test_tensor_core_logistic_logp_grad_is_fp32_accurate(tfp, B, N):
   elp_tc = np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64))
   elp_fp = np.max(np.abs(lp2.cpu().numpy() - lp64) / np.abs(lp64))
   assert elp_tc < 3 * max(elp_fp, 2e-6), (elp_tc, elp_fp)
+
+
+@pytest.mark.parametrize('D', [50, 77, 100])
+def test_tile_kernels_general_dense_gaussian_with_loc(tfp, D):
+  """The tensor-core tile kernels on a general dense Gaussian -- non-zero location, dimension not a multiple of the
+  13-dim thread segments (the padded columns must stay out of the contraction): gradient vs float64, HMC and NUTS vs
+  the oracle, asynchronous lanes == lock-step."""
+  from probability_b200 import _lib
+  rng = np.random.default_rng(D)
+  A = rng.standard_normal((D, D))
+  cov = A @ A.T / D + 0.3 * np.eye(D)
+  loc = (3.0 * rng.standard_normal(D)).astype(np.float32)
+  tg = tfp.targets.DenseGaussian(covariance=cov, loc=loc)
+  o32 = otargets.DenseGaussian(tg.precision, tg.log_normalizer, loc=loc)
+  B = 320
+  x0 = (loc + rng.standard_normal((B, D)) @ np.linalg.cholesky(cov).T).astype(np.float32)
+  ctx = _lib.Context.get(dev()); ctx.bind_stream()
+  # gradient primitive (tcgen05) vs float64
+  lp = torch.empty(B, device=dev()); g = torch.empty(B, D, device=dev())
+  _lib.check(ctx.lib.pb2_dense_logp_grad_tc(ctx.handle, tg.handle(ctx), B, _lib.ptr(t(x0)), _lib.ptr(lp), _lib.ptr(g)),
+             ctx.handle)
+  g64 = -((x0.astype(np.float64) - loc) @ tg.precision.astype(np.float64))
+  assert np.max(np.abs(g.cpu().numpy() - g64)) / np.abs(g64).max() < 2e-6
+  seed = orng.key(5)
+  lp0, g0 = o32.logp_grad(x0)
+  # HMC tile kernel vs oracle
+  k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.25, num_leapfrog_steps=4)
+  s, r = k.one_step(t(x0), k.bootstrap_results(t(x0)), seed=seed)
+  ref = omcmc.hmc_one_step(o32, x0, lp0, g0, 0.25, 4, seed)
+  agree = r.is_accepted.cpu().numpy() == ref['is_accepted']
+  assert agree.mean() > 0.97
+  np.testing.assert_allclose(s.cpu().numpy()[agree], ref['state'][agree], rtol=1e-4, atol=2e-3)
+  # NUTS: asynchronous lanes == lock-step bit for bit, and the oracle's trees
+  kn = tfp.mcmc.NoUTurnSampler(tg, step_size=0.3, max_tree_depth=7)
+  outs = {}
+  try:
+    for variant in (0, 3):
+      ctx.set_int('dense_variant', variant)
+      sn, rn = kn.one_step(t(x0), kn.bootstrap_results(t(x0)), seed=seed)
+      outs[variant] = (sn.cpu().numpy(), rn.leapfrogs_taken.cpu().numpy())
+  finally:
+    ctx.set_int('dense_variant', 0)
+  np.testing.assert_array_equal(outs[0][0], outs[3][0])
+  np.testing.assert_array_equal(outs[0][1], outs[3][1])
+  refn = omcmc.nuts_one_step(o32, x0, lp0, g0, 0.3, seed, max_tree_depth=7)
+  same = outs[0][1] == refn['leapfrogs_taken']
+  assert same.mean() >= 0.97
+  close = np.isclose(outs[0][0], refn['state'], rtol=2e-3, atol=2e-3).all(1)
+  assert close[same].mean() >= 0.97
