@@ -735,3 +735,20 @@ def test_tile_kernels_general_dense_gaussian_with_loc(tfp, D):
   assert same.mean() >= 0.97
   close = np.isclose(outs[0][0], refn['state'], rtol=2e-3, atol=2e-3).all(1)
   assert close[same].mean() >= 0.97
+
+
+def test_tile_nuts_async_burnin_and_thinning(tfp):
+  """sample.py:359-366 emission schedule on the asynchronous-lane kernel: burn-in steps are not emitted, thinning
+  picks every other state (hmc_test.py:91-140), traced fields line up with the states."""
+  tg, _, x0 = _dense100_state(384, seed=9)
+  k = tfp.mcmc.NoUTurnSampler(tg, step_size=0.7, max_tree_depth=7)
+  tr = lambda _, kr: (kr.leapfrogs_taken, kr.target_log_prob)
+  a = tfp.mcmc.sample_chain(8, t(x0), kernel=k, num_burnin_steps=3, trace_fn=tr, seed=31)
+  b = tfp.mcmc.sample_chain(4, t(x0), kernel=k, num_burnin_steps=3, num_steps_between_results=1, trace_fn=tr, seed=31)
+  np.testing.assert_array_equal(a.all_states.cpu().numpy()[::2], b.all_states.cpu().numpy())
+  np.testing.assert_array_equal(a.trace[0].cpu().numpy()[::2], b.trace[0].cpu().numpy())
+  np.testing.assert_array_equal(a.trace[1].cpu().numpy()[::2], b.trace[1].cpu().numpy())
+  # the traced log-prob is the log-prob of the emitted state
+  o32 = otargets.DenseGaussian(tg.precision, tg.log_normalizer)
+  lp, _ = o32.logp_grad(a.all_states[-1].cpu().numpy())
+  np.testing.assert_allclose(lp, a.trace[1][-1].cpu().numpy(), rtol=2e-4, atol=5e-2)
