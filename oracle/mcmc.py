@@ -516,6 +516,29 @@ class DualAveraging:
     return self.step_size
 
 
+class SimpleAdaptation:
+  """simple_step_size_adaptation.py:353-440 for one chain-shared scalar step size: the step is multiplied by
+  (1 + adaptation_rate) when the log-mean-exp accept prob exceeds log(target), divided otherwise, for the first
+  num_adaptation_steps steps (hmc_test.py:917-952 pins the count).  Same interface as DualAveraging."""
+
+  def __init__(self, step_size, num_adaptation_steps, target_accept_prob=0.75, adaptation_rate=0.01):
+    self.step_size = f32(step_size)
+    self.n_adapt = int(num_adaptation_steps)
+    self.log_target = np.log(f32(target_accept_prob))
+    self.one_plus = f32(1) + f32(adaptation_rate)
+    self.step = 0
+
+  def update(self, log_accept_ratio):
+    lar = np.asarray(log_accept_ratio, f32)
+    la = np.minimum(np.where(np.isfinite(lar), lar, NEG_INF), f32(0)).astype(f32)
+    r = DualAveraging.reduce_logmeanexp(la)
+    if self.step < self.n_adapt:
+      self.step_size = f32(self.step_size * self.one_plus) if r > self.log_target else \
+          f32(self.step_size / self.one_plus)
+    self.step += 1
+    return self.step_size
+
+
 # ----------------------------------------------------------------------------
 def sample_chain(target, kind, x0, num_results, num_burnin_steps=0, num_steps_between_results=0,
                  step_size=0.1, num_leapfrog_steps=3, max_tree_depth=10, max_energy_diff=1000.0,

@@ -90,18 +90,34 @@ def step_size_tensor(step_size, B, D, shapes, device):
     if len(parts) != len(sizes):
       raise ValueError('There should be exactly one `step_size` or it should have same length as '
                        '`current_state`.')
+    parts = [torch.as_tensor(s, dtype=torch.float32, device=device) for s in parts]
+    # per-chain forms ([B] + [1]*event_rank) in every part -> ONE per-chain step (they must agree: the kernels take
+    # one step size per chain); anything that broadcasts against the event shape -> per dimension
+    per_chain = [s.dim() == len(shp) + 1 and s.shape[0] == B and s.numel() == B for s, shp in zip(parts, shapes)]
+    if all(per_chain):
+      flat = [s.reshape(B) for s in parts]
+      for f in flat[1:]:
+        if not torch.equal(f, flat[0]):
+          raise ValueError('per-chain step sizes must be the same for every state part (the kernels take one '
+                           'step size per chain)')
+      return flat[0].contiguous().clone(), _lib.STEP_PER_CHAIN
     cols = []
     for s, n, shp in zip(parts, sizes, shapes):
-      s = torch.as_tensor(s, dtype=torch.float32, device=device)
-      cols.append(torch.broadcast_to(s, shp if len(shp) else (1,)).reshape(-1) if s.dim() <= len(shp)
-                  else s.reshape(-1))
-    return torch.cat(cols).contiguous(), _lib.STEP_PER_DIM
+      if s.dim() > len(shp):
+        raise ValueError('unsupported step_size part of shape {} for a state part of event shape {} ({} chains): '
+                         'a part must broadcast against the event shape, or every part must be per-chain '
+                         '[chains, 1, ...]'.format(tuple(s.shape), tuple(shp), B))
+      cols.append(torch.broadcast_to(s, shp if len(shp) else (1,)).reshape(-1))
+    out = torch.cat(cols).contiguous()
+    if out.numel() != D:
+      raise ValueError('per-part step sizes cover {} dimensions but the state has {}'.format(out.numel(), D))
+    return out, _lib.STEP_PER_DIM
   s = torch.as_tensor(step_size, dtype=torch.float32, device=device)
   if s.dim() == 0 or s.numel() == 1:
     return s.reshape(1).contiguous().clone(), _lib.STEP_SCALAR
   if s.dim() == 1 and s.shape[0] == D:
     return s.contiguous().clone(), _lib.STEP_PER_DIM
-  if (s.dim() == 2 and s.shape == (B, 1)) or (s.dim() == 1 and s.shape[0] == B):
+  if s.dim() >= 2 and s.shape[0] == B and s.numel() == B:
     return s.reshape(B).contiguous().clone(), _lib.STEP_PER_CHAIN
   raise ValueError('unsupported step_size shape {} for state [{}, {}]'.format(tuple(s.shape), B, D))
 

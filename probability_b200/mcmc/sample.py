@@ -141,9 +141,11 @@ def _try_fused(kernel, num_results, current_state, pkr, num_burnin_steps, num_st
   da_state = None
   step = None
   if da is not None:
+    if not da._is_scalar_case(pkr):
+      return None   # per-part / per-chain step sizes, custom getters: the reference's step loop (general update)
     inner_pkr = da.step_size_setter_fn(inner_pkr, pkr.new_step_size)
     da_state = da._pack(pkr)
-    step = pkr.new_step_size.reshape(1).float().contiguous().clone()
+    step = da_lib._flat(pkr.new_step_size)[0].reshape(1).float().contiguous().clone()
   res = inner._fused_run(x, shapes, was_list, inner_pkr, seed, num_results, num_burnin_steps,
                          num_steps_between_results, list(dict.fromkeys(inner_paths)), da_state=da_state,
                          step=step, leapfrog_total=leapfrog_total)
