@@ -17,6 +17,8 @@
  *   pb2_run (NUTS)       mcmc/nuts.py:321-445 NoUTurnSampler.one_step
  *   pb2_run (n_steps>1)  mcmc/sample.py:81-383 sample_chain (+ internal/loop_util.py:123-253)
  *   pb2_da_*             mcmc/dual_averaging_step_size_adaptation.py:353-532
+ *   pb2_comm_*           internal/distribute_lib.py:147-242 (named-axis psum / reduce_logsumexp) -> NCCL
+ *   pb2_rowshard_leapfrog  leapfrog_integrator.py:280-355 over a psum'd target (distribute_lib.py:179-242)
  *   pb2_ess / pb2_rhat   mcmc/diagnostic.py:38-336,339-567
  *
  * Conventions: every function returns 0 on success and a negative code on error
@@ -177,6 +179,10 @@ typedef struct {
 typedef struct {
   int enabled;                /* 0: fixed step size */
   float* d_state;             /* [16] device, from pb2_da_init */
+  int reduce_over_ranks;      /* 1: the chains are sharded over the ranks of the context's communicator (pb2_comm_init)
+                                 and the accept statistic is reduced over ALL of them inside pb2_run: one 2-float
+                                 all-gather per adapting transition, enqueued on the stream (no host round trip) --
+                                 experimental_reduce_chain_axis_names, dual_averaging_step_size_adaptation.py:259-261 */
 } pb2_da;
 
 /* Runs num_burnin + 1 + (R-1)*(1+thin) transitions for all B chains, chaining
@@ -185,9 +191,8 @@ typedef struct {
  * (nullable, [n_steps,2]) receives every transition's seed.  d_x/d_logp/d_grad hold
  * the chain state in and out.  d_step_size: scalar | [D] | [B] per cfg.step_kind; with
  * dual averaging enabled (scalar only) it is updated in place after every transition
- * and the reduction over chains is local to this process (single-GPU); multi-GPU
- * callers run adaptation transitions one at a time and combine pb2_da_partial
- * results across ranks themselves (see pb2_da_apply).
+ * and the reduction over chains spans this process's chains, or -- da->reduce_over_ranks with a
+ * communicator attached (pb2_comm_init) -- the chains of all ranks (every rank must make the same call).
  * d_leapfrog_total (nullable, uint64[B]) accumulates gradient evaluations. */
 int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* layout,
             const pb2_run_cfg* cfg, uint32_t h_seed[2], uint32_t* h_step_seeds, float* d_x,
@@ -242,6 +247,32 @@ int pb2_rowshard_logistic_finish(pb2_ctx* ctx, const float* d_packed, const floa
  * mode 2: v += eps g, m_out = v - (eps/2) g. */
 int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_step, int step_kind,
                           float* d_v, float* d_x, const float* d_g, const float* d_m_in, float* d_m_out);
+
+/* ---- multi-GPU group ------------------------------------------------------------------------
+ * One NCCL communicator per context (one process per GPU).  Replaces the named-axis collectives of
+ * internal/distribute_lib.py:147-242 (psum / reduce_logsumexp / pbroadcast) on this path:
+ *   - chain-sharded runs: dual-averaging statistics (pb2_run with da->reduce_over_ranks);
+ *   - row-sharded data : the per-leapfrog gradient psum inside pb2_rowshard_leapfrog.
+ * Rank 0 creates the id (pb2_comm_unique_id) and hands it to the other ranks by any transport (torch.distributed
+ * broadcast, MPI, a file); every rank then calls pb2_comm_init.  NCCL is bound at run time (dlopen). */
+#define PB2_COMM_ID_BYTES 128
+int pb2_comm_unique_id(void* out_id /* PB2_COMM_ID_BYTES host bytes */);
+int pb2_comm_init(pb2_ctx* ctx, int nranks, int rank, const void* nccl_unique_id);
+int pb2_comm_destroy(pb2_ctx* ctx);
+int pb2_comm_size(pb2_ctx* ctx);   /* 1 without a communicator */
+int pb2_comm_rank(pb2_ctx* ctx);
+/* in-place sum over the ranks, enqueued on the context's stream (parity surface of the collective) */
+int pb2_comm_allreduce_sum(pb2_ctx* ctx, float* d_buf, long long n);
+
+/* SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-355) for the row-sharded logistic regression, all chains in
+ * lock-step, ALL num_steps leapfrogs enqueued by this one call: per leapfrog the local gradient pass
+ * (d_planes != NULL: tcgen05, else the FP32 kernel on d_X), the all-reduce of the packed [B, D+1] buffer over the
+ * context's communicator (reduce_over_ranks != 0) and one fused kernel for prior + kick + drift.  Same argument meaning
+ * as pb2_leapfrog; outputs must not alias inputs. */
+int pb2_rowshard_leapfrog(pb2_ctx* ctx, const void* d_planes, const float* d_X, const float* d_y, int N, int D, int DP,
+                          int B, const float* d_m, const float* d_x, const float* d_logp, const float* d_grad,
+                          const float* d_step, int step_kind, int num_steps, int reduce_over_ranks, float* d_m_out,
+                          float* d_x_out, float* d_logp_out, float* d_grad_out);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,10 @@ class Trace(C.Structure):
 
 
 class DA(C.Structure):
-  _fields_ = [('enabled', C.c_int), ('d_state', C.c_void_p)]
+  _fields_ = [('enabled', C.c_int), ('d_state', C.c_void_p), ('reduce_over_ranks', C.c_int)]
+
+
+COMM_ID_BYTES = 128
 
 
 class Pb2Error(RuntimeError):
@@ -111,6 +114,14 @@ def load():
         'pb2_rowshard_logistic_grad_tc': ([vp, vp, vp, i32, i32, vp, i32, vp], i32),
         'pb2_rowshard_logistic_finish': ([vp, vp, vp, i32, i32, vp, vp], i32),
         'pb2_lockstep_leapfrog': ([vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp], i32),
+        'pb2_comm_unique_id': ([vp], i32),
+        'pb2_comm_init': ([vp, i32, i32, vp], i32),
+        'pb2_comm_destroy': ([vp], i32),
+        'pb2_comm_size': ([vp], i32),
+        'pb2_comm_rank': ([vp], i32),
+        'pb2_comm_allreduce_sum': ([vp, vp, ll], i32),
+        'pb2_rowshard_leapfrog': ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp],
+                                  i32),
     }
     for name, (argtypes, restype) in sig.items():
       try:

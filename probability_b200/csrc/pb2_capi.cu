@@ -75,7 +75,7 @@ int pb2_ctx_create(int device, pb2_ctx** out) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* v = getenv("PB2_DENSE_VARIANT")) c->dense_variant = atoi(v);
   if (int rc = check_cuda(c, cudaMalloc(&c->d_queue, 64), "cudaMalloc(queue)")) { delete c; return rc; }
-  if (int rc = check_cuda(c, cudaMalloc(&c->d_partial, 64), "cudaMalloc(partial)")) { delete c; return rc; }
+  if (int rc = check_cuda(c, cudaMalloc(&c->d_partial, 4096), "cudaMalloc(partial)")) { delete c; return rc; }
   *out = c;
   return PB2_OK;
 }
@@ -83,6 +83,8 @@ int pb2_ctx_create(int device, pb2_ctx** out) {
 int pb2_ctx_destroy(pb2_ctx* ctx) {
   if (!ctx) return PB2_OK;
   cudaSetDevice(ctx->device);
+  pb2_comm_destroy(ctx);
+  cudaFree(ctx->d_rs);
   cudaFree(ctx->d_queue);
   cudaFree(ctx->d_partial);
   cudaFree(ctx->d_ckpt);
@@ -294,6 +296,10 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
   const bool use_da = da && da->enabled;
   if (use_da && (cfg->step_kind != PB2_STEP_SCALAR || !da->d_state))
     return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_run: fused dual averaging needs a scalar step size");
+  const bool da_ranks = use_da && da->reduce_over_ranks && lay->B_global > lay->B;
+  if (da_ranks && (!ctx->comm || ctx->comm_size < 2))
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_run: da->reduce_over_ranks needs a communicator (pb2_comm_init)");
+  if (da_ranks && ctx->comm_size > 500) return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_run: more than 500 ranks");
   cudaSetDevice(ctx->device);
 
   const long long n_steps_ll = (long long)cfg->num_burnin_steps + 1 +
@@ -405,7 +411,11 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
       if (int rc2 = launch_chain(ctx, tgt, mode, p, io)) return rc2;
       if (adapting) {
         if (int rc2 = launch_da_partial(ctx, p.lar_last, lay->B, ctx->d_partial)) return rc2;
-        if (int rc2 = launch_da_apply(ctx, ctx->d_partial, 1, lay->B, da->d_state, d_step_size, nullptr)) return rc2;
+        if (da_ranks) {
+          // every rank gathers all (max, sum-exp) pairs and combines them in rank order: the same bits everywhere
+          if (int rc2 = comm_allgather(ctx, ctx->d_partial, ctx->d_partial + 2, 2)) return rc2;
+          if (int rc2 = launch_da_apply(ctx, ctx->d_partial + 2, ctx->comm_size, lay->B_global, da->d_state, d_step_size, nullptr)) return rc2;
+        } else if (int rc2 = launch_da_apply(ctx, ctx->d_partial, 1, lay->B, da->d_state, d_step_size, nullptr)) return rc2;
         da_step += 1;
       } else if (use_da) {
         da_advance_kernel<<<1, 32, 0, ctx->stream>>>(da->d_state, u_end - u);

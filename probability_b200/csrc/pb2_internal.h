@@ -25,7 +25,12 @@ struct pb2_ctx {
   size_t step_keys_bytes = 0;
   float* d_step_seq = nullptr;     // per-transition scalar step sizes (dual averaging)
   size_t step_seq_bytes = 0;
-  float* d_partial = nullptr;      // [2] dual-averaging partial
+  float* d_partial = nullptr;      // [2] dual-averaging partial, followed by [2 * comm_size] gathered partials
+  // multi-GPU group (pb2_comm.cu): NCCL communicator of this context (ncclComm_t), nullptr on a single GPU
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  float* d_rs = nullptr;           // row-sharded leapfrog scratch: v [B, D] + packed [B, D + 1]
+  size_t rs_bytes = 0;
 };
 
 struct pb2_target {
@@ -75,6 +80,10 @@ size_t rowshard_tc_planes_bytes(int N);
 int launch_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, unsigned char* d_planes);
 int launch_rowshard_tc(pb2_ctx* ctx, const unsigned char* d_planes, const float* d_y, int N, int D, const float* d_theta,
                        int B, float* d_packed);
+
+// pb2_comm.cu (no-ops / errors without a communicator)
+int comm_allreduce_sum(pb2_ctx* ctx, float* d_buf, size_t n);
+int comm_allgather(pb2_ctx* ctx, const float* d_send, float* d_recv, size_t n_per_rank);
 
 // pb2_misc.cu
 int launch_hmc_sched(pb2_ctx* ctx, const uint32_t* d_step_keys, int T, int n_parts, int layout, uint32_t* d_out);

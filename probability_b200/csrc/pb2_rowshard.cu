@@ -72,10 +72,10 @@ rowshard_logistic_kernel(const float* __restrict__ X, const float* __restrict__ 
       }
       const float z = (z0 + z1) + (z2 + z3);
       const float yn = ys[buf][r];
-      const float e = __expf(-fabsf(z));
-      const float rr = __fdividef(1.0f, 1.0f + e);
+      const float e = expf(-fabsf(z));                     // accurate forms: this log-likelihood feeds the MH test
+      const float rr = 1.0f / (1.0f + e);
       const float sg = z >= 0.f ? rr : e * rr;
-      ll += yn * z - (__logf(1.0f + e) + fmaxf(z, 0.f));   // bernoulli.py:119-135
+      ll += yn * z - (log1pf(e) + fmaxf(z, 0.f));          // bernoulli.py:119-135
       const float w = yn - sg;
 #pragma unroll
       for (int q = 0; q < DP / 4; ++q) {

@@ -128,7 +128,7 @@ ChainShard = collections.namedtuple('ChainShard', ['chain_offset', 'num_chains_g
 def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_burnin_steps=0,
         num_steps_between_results=0, seed=None, step_seeds=None, num_leapfrog_steps=1,
         max_tree_depth=10, max_energy_diff=1000.0, unrolled_leapfrog_steps=1, want=(),
-        da_state=None, shard=None, leapfrog_total=None, layout=None):
+        da_state=None, shard=None, leapfrog_total=None, layout=None, da_over_ranks=False):
   """Calls pb2_run.  x, lp, g, step are updated IN PLACE (pass clones to keep inputs).
   Returns (trace dict of tensors with leading R, final pass-along seed, step seeds)."""
   import torch
@@ -181,7 +181,8 @@ def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_bur
     out[name] = t
     setattr(tr, 'd_' + name, t.data_ptr())
   da = _lib.DA(enabled=0 if da_state is None else 1,
-               d_state=None if da_state is None else da_state.data_ptr())
+               d_state=None if da_state is None else da_state.data_ptr(),
+               reduce_over_ranks=1 if da_over_ranks else 0)
   rc = ctx.lib.pb2_run(ctx.handle, target.handle(ctx), C.byref(lay), C.byref(cfg), _lib.u32p(h_seed),
                        _lib.u32p(h_steps), _lib.ptr(x), _lib.ptr(lp), _lib.ptr(g), _lib.ptr(step),
                        C.byref(da), C.byref(tr), _lib.ptr(leapfrog_total))

@@ -287,9 +287,13 @@ class DualAveragingStepSizeAdaptation(kernel_base.TransitionKernel):
       ws = dist.get_world_size()
       gathered = torch.empty(ws, 2, dtype=torch.float32, device=lar.device)
       dist.all_gather_into_tensor(gathered, partial)
-      cnt = torch.tensor([float(lar.numel())], device=lar.device)
-      dist.all_reduce(cnt)
-      n_global = int(cnt.item())
+      shard = getattr(self.inner_kernel, 'chain_shard', None)
+      if shard is not None:
+        n_global = int(shard.num_chains_global)      # known on the host: no device round trip
+      else:
+        cnt = torch.tensor([float(lar.numel())], device=lar.device)
+        dist.all_reduce(cnt)
+        n_global = int(cnt.item())
       partial = gathered.contiguous()
     n_part = partial.numel() // 2
     _lib.check(ctx.lib.pb2_da_apply(ctx.handle, _lib.ptr(partial), n_part, n_global, _lib.ptr(st), None),

@@ -276,7 +276,8 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
   }
 
   def _fused_run(self, x, shapes, was_list, pkr, seed, num_results, num_burnin_steps,
-                 num_steps_between_results, paths, da_state=None, step=None, leapfrog_total=None):
+                 num_steps_between_results, paths, da_state=None, step=None, leapfrog_total=None,
+                 da_over_ranks=False):
     """Runs all transitions in libpb2; returns (trace dict keyed by results path, final results, seed)."""
     if self._lockstep:
       return None     # row-sharded target: the step loop drives the per-leapfrog all-reduce
@@ -298,7 +299,7 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
         self._target, x, lp, g, step, step_kind, shapes, kind=_lib.KERNEL_HMC, num_results=num_results,
         num_burnin_steps=num_burnin_steps, num_steps_between_results=num_steps_between_results, seed=seed,
         num_leapfrog_steps=L, want=tuple(want), da_state=da_state, shard=self.chain_shard,
-        leapfrog_total=leapfrog_total)
+        leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks)
     traced = {}
     for p in paths:
       v = out[self._FUSED_FIELDS[p]] if self._FUSED_FIELDS[p] in out else None

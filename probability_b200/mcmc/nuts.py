@@ -145,7 +145,8 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
   _FUSED_FIELDS = {(f,): f for f in _ALL + ('step_size',)}
 
   def _fused_run(self, x, shapes, was_list, pkr, seed, num_results, num_burnin_steps,
-                 num_steps_between_results, paths, da_state=None, step=None, leapfrog_total=None):
+                 num_steps_between_results, paths, da_state=None, step=None, leapfrog_total=None,
+                 da_over_ranks=False):
     B, D = x.shape
     g = _engine.flatten_state(list(pkr.grads_target_log_prob))[0].clone()
     lp = pkr.target_log_prob.contiguous().clone()
@@ -164,7 +165,7 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
         num_burnin_steps=num_burnin_steps, num_steps_between_results=num_steps_between_results, seed=seed,
         max_tree_depth=self.max_tree_depth, max_energy_diff=self.max_energy_diff,
         unrolled_leapfrog_steps=self.unrolled_leapfrog_steps, want=tuple(want), da_state=da_state,
-        shard=self.chain_shard, leapfrog_total=leapfrog_total)
+        shard=self.chain_shard, leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks)
     traced = {}
     for p in paths:
       v = out.get(self._FUSED_FIELDS[p])

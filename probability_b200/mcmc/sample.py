@@ -98,7 +98,14 @@ def _fused_kernel(kernel):
   if isinstance(kernel, da_lib.DualAveragingStepSizeAdaptation) and isinstance(
       kernel.inner_kernel, (hmc_lib.HamiltonianMonteCarlo, nuts_lib.NoUTurnSampler)):
     if kernel._world() is not None:
-      return None  # cross-rank reduction every step: run the step loop
+      # chains sharded over ranks: fused only when the library owns the collective (distribute.init_comm);
+      # otherwise the step loop with torch.distributed collectives
+      from probability_b200 import distribute
+      try:
+        if distribute.comm_size() != kernel._world().get_world_size():
+          return None
+      except _lib.Pb2Error:
+        return None
     return kernel.inner_kernel, kernel
   return None
 
@@ -148,7 +155,8 @@ def _try_fused(kernel, num_results, current_state, pkr, num_burnin_steps, num_st
     step = da_lib._flat(pkr.new_step_size)[0].reshape(1).float().contiguous().clone()
   res = inner._fused_run(x, shapes, was_list, inner_pkr, seed, num_results, num_burnin_steps,
                          num_steps_between_results, list(dict.fromkeys(inner_paths)), da_state=da_state,
-                         step=step, leapfrog_total=leapfrog_total)
+                         step=step, leapfrog_total=leapfrog_total,
+                         da_over_ranks=(da is not None and da._world() is not None))
   if res is None:
     return None
   states, traced, final_inner, seed_out = res

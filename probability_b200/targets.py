@@ -237,19 +237,45 @@ class RowShardedLogisticRegression(Target):
                                                     self.padded_dim, _lib.ptr(x), B, _lib.ptr(packed)), ctx.handle)
     dist = self._world()
     if dist is not None:
-      dist.all_reduce(packed, group=self.process_group)     # per-leapfrog gradient all-reduce (NCCL/NVLink)
+      if self._library_owns_collective(ctx):
+        _lib.check(ctx.lib.pb2_comm_allreduce_sum(ctx.handle, _lib.ptr(packed), packed.numel()), ctx.handle)
+      else:
+        dist.all_reduce(packed, group=self.process_group)     # per-leapfrog gradient all-reduce (NCCL/NVLink)
     lp = torch.empty(B, dtype=torch.float32, device=x.device)
     g = torch.empty_like(x)
     _lib.check(ctx.lib.pb2_rowshard_logistic_finish(ctx.handle, _lib.ptr(packed), _lib.ptr(x), B, self.dim,
                                                     _lib.ptr(g), _lib.ptr(lp)), ctx.handle)
     return lp, g
 
+  def _library_owns_collective(self, ctx):
+    """True when the per-leapfrog all-reduce can be issued by libpb2 itself: single rank, or a communicator of the
+    group's size attached to the context (distribute.init_comm)."""
+    dist = self._world()
+    if dist is None:
+      return True
+    return int(ctx.lib.pb2_comm_size(ctx.handle)) == dist.get_world_size(self.process_group)
+
   def leapfrog(self, m, x, lp, g, step, step_kind, num_steps):
-    """SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-309) lock-step over all chains."""
+    """SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-309) lock-step over all chains.  ONE C-ABI call
+    (pb2_rowshard_leapfrog) enqueues all leapfrogs -- gradient kernel, NCCL all-reduce, fused prior + kick + drift --
+    when the library owns the collective; otherwise the per-leapfrog loop below with torch.distributed."""
     import torch
     ctx = _lib.Context.get(x.device)
     ctx.bind_stream()
     B, D = x.shape
+    if self._library_owns_collective(ctx):
+      X, y = self._device_data(x.device)
+      use_tc = B >= 128 and self.use_tensor_cores
+      planes = self._tc_planes(ctx, x.device) if use_tc else None
+      m_out, x_out, g_out = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+      lp_out = torch.empty(B, dtype=torch.float32, device=x.device)
+      _lib.check(ctx.lib.pb2_rowshard_leapfrog(
+          ctx.handle, _lib.ptr(planes), _lib.ptr(X), _lib.ptr(y), self.n_rows, self.dim, self.padded_dim, B,
+          _lib.ptr(m.contiguous()), _lib.ptr(x.contiguous()), _lib.ptr(lp.contiguous()), _lib.ptr(g.contiguous()),
+          _lib.ptr(step), step_kind, int(num_steps), 0 if self._world() is None else 1, _lib.ptr(m_out),
+          _lib.ptr(x_out), _lib.ptr(lp_out),
+          _lib.ptr(g_out)), ctx.handle)
+      return m_out, x_out, lp_out, g_out
     x = x.clone()
     v = torch.empty_like(x)
     m_out = torch.empty_like(x)

@@ -1,4 +1,6 @@
-"""Run under torchrun on >= 2 GPUs (one process per GPU, NCCL):
+"""Run under torchrun on >= 2 GPUs (one process per GPU, NCCL), once with the collectives issued from Python
+(torch.distributed) and once with the library-owned communicator (tfp.distribute.init_comm: fused sharded dual
+averaging inside pb2_run, per-leapfrog all-reduce inside pb2_rowshard_leapfrog):
   (a) chain-sharded NUTS + DualAveraging == the unsharded run (global-chain-index RNG counters, cross-rank
       log-mean-exp): same step sizes on every rank, same states bit for bit;
   (b) row-sharded logistic HMC with the per-leapfrog gradient all-reduce == all rows on one GPU, and all
@@ -22,7 +24,22 @@ def main():
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   dist.init_process_group('nccl', device_id=dev)
+  for mode in ('torch.distributed collectives', 'library-owned communicator'):
+    if mode.startswith('library'):
+      assert tfp.distribute.init_comm() == world
+      assert tfp.distribute.comm_size() == world
+      t = torch.full((5,), float(rank + 1), device=dev)
+      tfp.distribute.all_reduce_sum(t)
+      assert torch.equal(t, torch.full((5,), world * (world + 1) / 2.0, device=dev))
+    check(rank, world, dev, mode)
+  dist.barrier()
+  if rank == 0:
+    print('MULTIGPU OK world=%d' % world, flush=True)
+  tfp.distribute.destroy_comm()
+  dist.destroy_process_group()
 
+
+def check(rank, world, dev, mode):
   # ---------------- (a) chain sharding
   Bg = 64 * world
   B = Bg // world
@@ -84,8 +101,7 @@ def main():
       assert torch.equal(a, sh.all_states)
   dist.barrier()
   if rank == 0:
-    print('MULTIGPU OK world=%d' % world, flush=True)
-  dist.destroy_process_group()
+    print('multi-GPU invariants hold with %s' % mode, flush=True)
 
 
 if __name__ == '__main__':
