@@ -152,6 +152,9 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-ess', action='store_true')
   ap.add_argument('--step-size', type=float, default=None, help='skip dual averaging (profiling runs)')
+  ap.add_argument('--configs', default='all',
+                  help="per_config legs: 'all' (N=1: c1,c3,c4,c5; N>1: the sharded configs c3,c5), 'none', or a "
+                       "comma list of c1,c3,c4,c5")
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -168,6 +171,12 @@ def main():
     if rank != 0:
       return
     cb, done, dt = cpu_reference_arm(args.steps, args.warmup)
+    # the CPU arm runs a bounded SAMPLE of the workload: say so in its own config instead of echoing the GPU arm's
+    config = dict(config, chains_per_gpu=1024, chains_total=1024,
+                  workload=config['workload'].replace('%d chains per GPU' % args.chains,
+                                                      'bounded CPU sample: 1,024 of the %d chains' % args.chains),
+                  parallelism='host cores (BLAS threads)', l2='n/a (CPU)',
+                  init='exact target draws; fixed step size 0.7 (what dual averaging finds on the GPU arm)')
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': done, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / max(done, 1),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -184,8 +193,15 @@ def main():
     raise SystemExit('bench.py needs a CUDA device (B200); there is no CPU fallback for the product path.')
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
+  shard_parity = None
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
+    # the library owns the on-path collectives (NCCL communicator attached to the context); before any timing, the
+    # sharded runs are checked against the unsharded job on every rank
+    import bench_configs
+    pk0, pk0_src = peaks()
+    shard_parity = bench_configs.shard_parity(tfp, bench_configs.Env(dev, rank, world, pk0, pk0_src))
+    log('[rank %d] shard_parity: %s' % (rank, shard_parity))
   B = args.chains
   shard = tfp.mcmc.ChainShard(chain_offset=rank * B, num_chains_global=world * B)
   target = tfp.targets.IllConditionedGaussian(ndims=D)
@@ -361,6 +377,27 @@ def main():
                 'note': 'ESS on 2,048 of the chains scaled to all chains of rank 0'}
     del draws, sub
 
+  # ---- the other named configs (bounded), every rank takes part in the sharded ones
+  per_config = {}
+  if args.configs != 'none':
+    import bench_configs
+    pk1, pk1_src = peaks()
+    env = bench_configs.Env(dev, rank, world, pk1, pk1_src)
+    want = (['c1', 'c3', 'c4', 'c5'] if world == 1 else ['c3', 'c5']) if args.configs == 'all' else args.configs.split(',')
+    del flush
+    torch.cuda.empty_cache()
+    for name in want:
+      if world > 1 and name in ('c1', 'c4'):
+        continue
+      t0 = time.perf_counter()
+      try:
+        per_config[name] = getattr(bench_configs, 'run_' + name)(tfp, env, cpu=not args.no_cpu_baseline)
+      except Exception as e:  # pylint: disable=broad-except
+        per_config[name] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+      log('[rank %d] %s: %.1fs %s' % (rank, name, time.perf_counter() - t0,
+                                      {k: v for k, v in per_config[name].items() if k in ('value', 'error', 'min_ess_per_sec')}))
+      torch.cuda.empty_cache()
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -399,7 +436,11 @@ def main():
           'timed_reps_ms': [1e3 * r[0] for r in reps],
           'per_launch_run': {'value': fused_value, 'unit': UNIT,
                              'note': 'same K transitions as K one_step launches, L2 flushed between launches'},
-          'min_ess': ess_info}
+          'min_ess': ess_info, 'per_config': per_config}
+  if ess_info:
+    line['min_ess_per_sec'] = ess_info['min_ess_per_sec_cross_chain']
+  if shard_parity is not None:
+    line['shard_parity'] = shard_parity
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
