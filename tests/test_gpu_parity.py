@@ -180,6 +180,8 @@ def test_leapfrog_trajectory_1e5(tfp, which, eps, L):
   m64 = v - 0.5 * e * gg
   r32 = omcmc.leapfrog(o32, m, x, lp0, g0, np.full(x.shape, eps, np.float32), L)
   base = max(rel_err(r32[1], xx64), 1e-6)
+  print('leapfrog %s: rel err vs float64 trajectory: x %.2e (float32 oracle %.2e), m %.2e, lp %.2e' % (
+      which, rel_err(ox.cpu().numpy(), xx64), base, rel_err(om.cpu().numpy(), m64), rel_err(ol.cpu().numpy(), ll)))
   assert rel_err(ox.cpu().numpy(), xx64) < max(1e-5, 3 * base)
   base_m = max(rel_err(r32[0], m64), 1e-6)
   assert rel_err(om.cpu().numpy(), m64) < max(1e-5, 3 * base_m)
@@ -285,11 +287,14 @@ def test_nuts_one_step_matches_oracle(tfp, which, eps, depth, layout):
     ref = omcmc.nuts_one_step(o32, x, lp0, g0, eps, seed, max_tree_depth=depth, layout=layout)
     nl = kr.leapfrogs_taken.cpu().numpy()
     same = nl == ref['leapfrogs_taken']
-    # float rounding may flip a U-turn / multinomial comparison for a few chains
-    assert same.mean() >= 0.9, (nl, ref['leapfrogs_taken'])
+    # float rounding may flip a U-turn / multinomial comparison for a few chains (measured in round 2: 64 of 64
+    # identical trees for every target and layout but one flip in one case)
+    print('NUTS %s layout %d: identical trees %.4f' % (which, layout, same.mean()))
+    assert same.mean() >= 0.97, (nl, ref['leapfrogs_taken'])
     got = _flat(new_state)
     close = np.isclose(got, ref['state'], rtol=2e-3, atol=2e-3).all(axis=1)
-    assert (close[same]).mean() >= 0.9
+    print('   states close on identical trees %.4f' % close[same].mean())
+    assert (close[same]).mean() >= 0.97
     for f in ('is_accepted', 'reach_max_depth', 'has_divergence'):
       assert (getattr(kr, f).cpu().numpy() == ref[f])[same & close].all(), f
     np.testing.assert_allclose(kr.log_accept_ratio.cpu().numpy()[same & close],
