@@ -11,7 +11,11 @@
 // the contraction.  13 dims per thread instead of 26 halve that work, and x, m, g, rho (52 registers) stay in
 // registers without spills.  The contraction itself costs the same (the zero half-rows ride along).
 // Per-chain scalars are replicated in the 8 threads of a chain and stay bit-identical because cross-part sums go
-// through shared memory in a fixed order.
+// through shared memory in a fixed order.  The 8 threads of chain c sit in rows c and c + 64, i.e. in the 8 warps with
+// (warp & 1) == ((c >> 5) & 1): the half-row exchange and the cross-part reductions synchronise only those 256 threads
+// (named barrier 1 + (warp & 1)), so the two halves of the tile drift apart between contractions instead of waiting
+// for each other at every reduction.  (Putting both half-rows of a chain into one warp -- exchange by shuffle -- does
+// not work: tcgen05.ld/st take ONE column address per warp, and the halves own different columns.)
 #pragma once
 #include "pb2_tile.cuh"
 
@@ -35,7 +39,7 @@ constexpr int kK = 13;        // dims per thread
 constexpr int kKP = tile::kKP, kNP = tile::kNP, kThreads = tile::kThreads;
 constexpr int kColAhi = tile::kColAhi, kColAlo = tile::kColAlo, kColD = tile::kColD;
 constexpr int kPlaneBytes = tile::kPlaneBytes;
-constexpr int kRedN = 4;
+constexpr int kRedN = 6;
 constexpr size_t kVS = (size_t)kKP * kM;   // floats per scratch vector of a tile
 
 // compile-time loop over the chunks (offset, length) that tile the 13 columns of a part
@@ -99,7 +103,7 @@ struct Ctx {
   float* xbuf;
   uint32_t tmem, lane_addr, idesc, phase;
   uint64_t bdesc_hi, bdesc_lo;
-  int cl, slice, half, part, parity;
+  int cl, slice, half, part, parity, group;
 
   // One-time setup: TMEM allocation, mbarrier, P hi/lo planes (canonical layout), loc, zero A.
   __device__ void init(Shared* sh_, unsigned char* planes, float* xbuf_, const float* P, const float* loc, int D) {
@@ -111,6 +115,7 @@ struct Ctx {
     half = row >> 6;
     slice = warp >> 2;
     part = 2 * slice + half;
+    group = warp & 1;
     parity = 0;
     phase = 0;
     if (warp == 0) {
@@ -239,7 +244,7 @@ struct Ctx {
     xw[kM] = make_float4(__uint_as_float(b0[4]), __uint_as_float(b0[5]), __uint_as_float(b0[6]), __uint_as_float(b0[7]));
     xw[2 * kM] = make_float4(__uint_as_float(b1[0]), __uint_as_float(b1[1]), __uint_as_float(b1[2]), __uint_as_float(b1[3]));
     reinterpret_cast<float*>(xw + 3 * kM)[0] = __uint_as_float(b2[0]);
-    __syncthreads();
+    group_sync();
     const float4* xr = reinterpret_cast<const float4*>(xbuf) + (size_t)part * 4 * kM + cl;
     const float4 r0 = xr[0], r1 = xr[kM], r2 = xr[2 * kM];
     const float r3 = reinterpret_cast<const float*>(xr + 3 * kM)[0];
@@ -252,7 +257,10 @@ struct Ctx {
     g[12] = __uint_as_float(a2[0]) + r3;
   }
 
-  // cross-part sums (fixed order => the 8 threads of a chain get identical bits); one barrier
+  // the 256 threads that own chains with ((c >> 5) & 1) == group
+  __device__ __forceinline__ void group_sync() const { asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory"); }
+
+  // cross-part sums (fixed order => the 8 threads of a chain get identical bits); one group barrier
   template <int N>
   __device__ __forceinline__ void reduce(float (&v)[N]) {
     static_assert(N <= kRedN, "too many simultaneous reductions");
@@ -260,7 +268,7 @@ struct Ctx {
     parity ^= 1;
 #pragma unroll
     for (int i = 0; i < N; ++i) buf[i][part][cl] = v[i];
-    __syncthreads();
+    group_sync();
 #pragma unroll
     for (int i = 0; i < N; ++i)
       v[i] = (((buf[i][0][cl] + buf[i][1][cl]) + (buf[i][2][cl] + buf[i][3][cl])) +

@@ -154,17 +154,19 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
       }
     }
   }
-  // last half kick, rho_subtree, checkpoint store / first U-turn check (nuts.py:826-869, 949-1010)
-  float s4[4] = {0.f, 0.f, 0.f, 0.f};   // <x - mu, g>, |m|^2, U-turn dots against the previous leaf's checkpoint
+  // last half kick, rho_subtree, checkpoint store / U-turn checks of the closing 2- and 4-leaf subtrees
+  // (nuts.py:826-869, 949-1010)
+  float s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // <x - mu, g>, |m|^2, dots vs the previous leaf, dots vs slot pc - 2
   const int pc = __popc(i);
   const bool odd = (i & 1) != 0;
   const int ones = __ffs(~i) - 1;          // trailing ones: the leaf closes subtrees of 2, 4, .., 2^ones leaves
+  const bool slot1 = odd && ones >= 2;     // (tile-uniform) the 4-leaf subtree closes: its checkpoint is slot pc - 2
   if (act) {
 #pragma unroll
     for (int j = 0; j < kK; ++j) {
       m[j] = m[j] - heps * g[j];
-      s4[0] = fmaf(x[j] - e.lc[j], g[j], s4[0]);
-      s4[1] = fmaf(m[j], m[j], s4[1]);
+      s6[0] = fmaf(x[j] - e.lc[j], g[j], s6[0]);
+      s6[1] = fmaf(m[j], m[j], s6[1]);
     }
     if (!odd) {
       seg_stv(e.ckl, cl, m);
@@ -187,21 +189,33 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
         const float diff = rho[j] - kr[j];
-        s4[2] = fmaf(diff, km[j], s4[2]);
-        s4[3] = fmaf(diff, m[j], s4[3]);
+        s6[2] = fmaf(diff, km[j], s6[2]);
+        s6[3] = fmaf(diff, m[j], s6[3]);
+      }
+      if (slot1) {   // same reduction: one barrier less on every fourth leaf
+        seg_ldv(e.ck_m + (size_t)(pc - 2) * kVS, cl, km);
+        seg_ldv(e.ck_r + (size_t)(pc - 2) * kVS, cl, kr);
+#pragma unroll
+        for (int j = 0; j < kK; ++j) {
+          const float diff = rho[j] - kr[j];
+          s6[4] = fmaf(diff, km[j], s6[4]);
+          s6[5] = fmaf(diff, m[j], s6[5]);
+        }
       }
     }
   }
   pf.mark(3);
-  cx.reduce<4>(s4);
+  if (slot1) cx.reduce<6>(s6);
+  else cx.reduce<4>(reinterpret_cast<float(&)[4]>(s6));
   pf.mark(4);
   bool ok = true;
   if (odd) {
-    if (jmax >= 1) ok = (s4[2] >= 0.f) && (s4[3] >= 0.f);
-    // the larger subtrees this leaf closes: slots [pc - ones, pc - 1), two checks per reduction
+    if (jmax >= 1) ok = (s6[2] >= 0.f) && (s6[3] >= 0.f);
+    if (slot1 && jmax >= 2) ok = ok && (s6[4] >= 0.f) && (s6[5] >= 0.f);
+    // the larger subtrees this leaf closes: slots [pc - ones, pc - 2), two checks per reduction
 #pragma unroll 1
-    for (int k = pc - ones; k < pc - 1; k += 2) {   // uniform trip count over the tile (shared leaf clock)
-      const bool two = k + 1 < pc - 1;
+    for (int k = pc - ones; k < pc - 2; k += 2) {   // uniform trip count over the tile (shared leaf clock)
+      const bool two = k + 1 < pc - 2;
       const int k1 = two ? k + 1 : k;
       float sd[4] = {0.f, 0.f, 0.f, 0.f};
       if (act)
@@ -209,7 +223,7 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
                    cl, rho, m, sd);
       cx.reduce<4>(sd);
       if (pc - k <= jmax) ok = ok && (sd[0] >= 0.f) && (sd[1] >= 0.f);
-      if (pc - k1 <= jmax) ok = ok && (sd[2] >= 0.f) && (sd[3] >= 0.f);
+      if (two && pc - k1 <= jmax) ok = ok && (sd[2] >= 0.f) && (sd[3] >= 0.f);
     }
     // async kernel, last leaf of a 32-leaf chunk: the subtrees of 64, 128, .. leaves it closes start at the first
     // leaf of an earlier chunk of this lane's doubling
@@ -236,8 +250,8 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
   pf.mark(5);
   if (act) {
     s.n += 1;
-    s.slp = fmaf(0.5f, s4[0], e.lognorm);
-    float en = s.slp - 0.5f * s4[1];                      // nuts.py:871-877
+    s.slp = fmaf(0.5f, s6[0], e.lognorm);
+    float en = s.slp - 0.5f * s6[1];                      // nuts.py:871-877
     en = isnan(en) ? -INFINITY : en;
     const float dH = en - H0;
     const bool nd_i = (-dH) < e.max_energy_diff;          // :880
