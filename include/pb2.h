@@ -150,6 +150,13 @@ typedef struct {
   int step_kind;            /* PB2_STEP_* */
   int explicit_step_seeds;  /* 0: derive per-transition seeds from h_seed (sample_chain);
                                1: h_step_seeds [n_steps,2] is an INPUT (TransitionKernel.one_step) */
+  const float* d_momentum_scale; /* NULL, or [D] device: s = sqrt of the diagonal INVERSE mass matrix (the running
+                               variance): momentum ~ N(0, diag(1/s^2)), kinetic energy 1/2 sum s^2 m^2, positions move
+                               along the velocity s^2 m, U-turn test on <rho, velocity> -- PreconditionedHamiltonianMonteCarlo /
+                               PreconditionedNoUTurnSampler with the momentum distribution DiagonalMassMatrixAdaptation
+                               builds (experimental/mcmc/preconditioned_hmc.py, preconditioned_nuts.py:169,
+                               diagonal_mass_matrix_adaptation.py:73).  States, gradients and momenta cross the ABI in
+                               the ORIGINAL coordinates; inside, the kernels run on u = x / s (pb2_targets.cuh). */
 } pb2_run_cfg;
 
 /* Nullable per-result outputs; leading dimension R = num_results.
@@ -212,6 +219,12 @@ int pb2_da_partial(pb2_ctx* ctx, const float* d_log_accept_ratio, int B, float* 
 /* combine n_partials (max,sumexp) pairs, update the state and write the new step size */
 int pb2_da_apply(pb2_ctx* ctx, const float* d_partials /*[n,2]*/, int n_partials, long long B_global,
                  float* d_state, float* d_step_size_out /* nullable */);
+
+/* ---- streaming moments (experimental/stats/sample_stats.py RunningVariance; the reducer behind
+ * DiagonalMassMatrixAdaptation and experimental/mcmc/with_reductions.py VarianceReducer) --------------------- */
+/* d_state [1 + 2 D] = (count, mean[D], sum of squared deviations[D]), zero-initialised by the caller; every row of
+ * d_x [rows, D] is one new observation (chains and draws alike).  variance = state[1 + D + d] / count. */
+int pb2_running_moments_update(pb2_ctx* ctx, const float* d_x, long long rows, int D, float* d_state);
 
 /* ---- diagnostics ------------------------------------------------------------------- */
 /* states [N,B,D] -> ess: cross_chain ? [D] : [B,D].  filter_threshold NaN = None;

@@ -60,13 +60,18 @@ def _uniform_b(k, B, layout, chain_offset=0, B_global=None):
 
 
 # ----------------------------------------------------------------------------
-def leapfrog(target, m, x, lp, g, eps, L):
-  """leapfrog_integrator.py:280-309 (+ _one_step :330-355); eps is [B,D] (signed)."""
+def leapfrog(target, m, x, lp, g, eps, L, inv_mass=None):
+  """leapfrog_integrator.py:280-309 (+ _one_step :330-355); eps is [B,D] (signed).  `inv_mass` [D]: diagonal of the
+  inverse mass matrix -- the position moves along the VELOCITY inv_mass * momentum, the gradient of the kinetic energy
+  (kinetic_energy_fn hook :267-275; experimental/mcmc/preconditioned_hmc.py, preconditioning_utils.py)."""
   m = np.asarray(m, f32); x = np.asarray(x, f32); g = np.asarray(g, f32)
   h = (f32(0.5) * eps).astype(f32)
   v = (m + h * g).astype(f32)
   for _ in range(int(L)):
-    x = (x + eps * v).astype(f32)
+    if inv_mass is None:
+      x = (x + eps * v).astype(f32)
+    else:
+      x = (x + eps * (f32(1) * inv_mass * v).astype(f32)).astype(f32)
     lp, g = target.logp_grad(x)
     v = (v + eps * g).astype(f32)
   m = (v - h * g).astype(f32)
@@ -83,19 +88,27 @@ def safe_sum(terms):
 
 
 def hmc_one_step(target, x, lp, g, step_size, L, seed, layout=orng.PARTITIONABLE,
-                 chain_offset=0, B_global=None):
+                 chain_offset=0, B_global=None, inv_mass=None):
   """HamiltonianMonteCarlo.one_step = MetropolisHastings(UncalibratedHMC).
-  Returns dict with next state/results and the proposal details."""
+  Returns dict with next state/results and the proposal details.  `inv_mass` [D] (diagonal inverse mass matrix =
+  running variance): PreconditionedHamiltonianMonteCarlo with the momentum distribution of
+  DiagonalMassMatrixAdaptation (experimental/mcmc/diagonal_mass_matrix_adaptation.py:73,
+  MultivariateNormalPrecisionFactorLinearOperator with precision factor diag(sqrt(variance))): momentum = z / sqrt(var),
+  kinetic energy 1/2 sum var m^2, velocity var m."""
   x = np.asarray(x, f32)
   B, D = x.shape
   prop, acc = orng.split(seed, 2, layout)                         # metropolis_hastings.py:183
   part_keys = orng.split(prop, len(target.part_sizes), layout)    # hmc.py:685
   m0 = draw_momentum(part_keys, B, target.part_sizes, layout, chain_offset, B_global)
+  if inv_mass is not None:
+    inv_mass = np.asarray(inv_mass, f32)
+    m0 = (m0 / np.sqrt(inv_mass).astype(f32)).astype(f32)
   eps = _step_b(step_size, B, D)
-  m1, x1, lp1, g1 = leapfrog(target, m0, x, lp, g, eps, L)
+  m1, x1, lp1, g1 = leapfrog(target, m0, x, lp, g, eps, L, inv_mass)
   with np.errstate(invalid='ignore', over='ignore'):
-    k0 = np.sum(m0 * m0, axis=1, dtype=f32)
-    k1 = np.sum(m1 * m1, axis=1, dtype=f32)
+    w = f32(1) if inv_mass is None else inv_mass
+    k0 = np.sum(w * m0 * m0, axis=1, dtype=f32)
+    k1 = np.sum(w * m1 * m1, axis=1, dtype=f32)
     corr = f32(0.5) * safe_sum([k0, -k1])                         # hmc.py:862-875
     ratio = safe_sum([lp1, -np.asarray(lp, f32), corr])           # metropolis_hastings.py:204-215
     u = _uniform_b(acc, B, layout, chain_offset, B_global)
@@ -185,24 +198,29 @@ def _dot(a, b):
   return np.sum(a * b, axis=1, dtype=f32)
 
 
-def _energy(lp, m):
-  """compute_hamiltonian nuts.py:1085-1102."""
+def _energy(lp, m, inv_mass=None):
+  """compute_hamiltonian nuts.py:1085-1102 (preconditioned: kinetic energy 1/2 sum inv_mass m^2, up to the constant of
+  the momentum distribution's log-prob, which cancels in every energy difference)."""
   with np.errstate(invalid='ignore', over='ignore'):
-    return (lp - f32(0.5) * np.sum(m * m, axis=1, dtype=f32)).astype(f32)
+    w = f32(1) if inv_mass is None else inv_mass
+    return (lp - f32(0.5) * np.sum(w * m * m, axis=1, dtype=f32)).astype(f32)
 
 
 def nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth=10,
                   max_energy_diff=1000.0, unrolled_leapfrog_steps=1,
                   layout=orng.PARTITIONABLE, chain_offset=0, B_global=None,
-                  count_grad_evals=None):
-  """Batched, lock-step NoUTurnSampler.one_step (nuts.py:321-445), literal masks."""
+                  count_grad_evals=None, inv_mass=None):
+  """Batched, lock-step NoUTurnSampler.one_step (nuts.py:321-445), literal masks.  `inv_mass` [D]: the
+  PreconditionedNoUTurnSampler with a diagonal mass matrix (experimental/mcmc/preconditioned_nuts.py:169): momentum
+  = z / sqrt(inv_mass), positions move along the velocity inv_mass * m, and the U-turn criterion dots the cumulative
+  MOMENTUM with the end VELOCITIES (:694-705, :964-1030)."""
   with np.errstate(all='ignore'):   # stopped chains keep integrating in lock-step and may overflow
     return _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy_diff,
-                          unrolled_leapfrog_steps, layout, chain_offset, B_global, count_grad_evals)
+                          unrolled_leapfrog_steps, layout, chain_offset, B_global, count_grad_evals, inv_mass)
 
 
 def _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy_diff,
-                   unrolled_leapfrog_steps, layout, chain_offset, B_global, count_grad_evals):
+                   unrolled_leapfrog_steps, layout, chain_offset, B_global, count_grad_evals, inv_mass=None):
   x = np.asarray(x, f32); lp = np.asarray(lp, f32); g = np.asarray(g, f32)
   B, D = x.shape
   write_instr, read_instr = write_read_closed_form(max_tree_depth)
@@ -210,7 +228,11 @@ def _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy
   k_start, k_loop = orng.split(seed, 2, layout)                         # :323
   ks = orng.split(k_start, len(target.part_sizes) + 1, layout)          # :515
   m = draw_momentum(ks[:-1], B, target.part_sizes, layout, chain_offset, B_global)
-  H0 = _energy(lp, m)                                                    # :524
+  vel = (lambda mm: mm) if inv_mass is None else (lambda mm: (np.asarray(inv_mass, f32) * mm).astype(f32))
+  if inv_mass is not None:
+    inv_mass = np.asarray(inv_mass, f32)
+    m = (m / np.sqrt(inv_mass).astype(f32)).astype(f32)
+  H0 = _energy(lp, m, inv_mass)                                          # :524
   # [2,B,...] ends: index 0 = left, 1 = right (:344-355)
   end_m = np.stack([m, m]); end_x = np.stack([x, x])
   end_lp = np.stack([lp, lp]); end_g = np.stack([g, g])
@@ -247,7 +269,7 @@ def _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy
     esum_sub = np.zeros(B, f32)
     while i < nsteps and c_prev.any():                                   # :759
       k_u, kk = orng.split(kk, 2, layout)                                # :808
-      s_m, s_x, s_lp, s_g = leapfrog(target, s_m, s_x, s_lp, s_g, eps, unrolled_leapfrog_steps)
+      s_m, s_x, s_lp, s_g = leapfrog(target, s_m, s_x, s_lp, s_g, eps, unrolled_leapfrog_steps, inv_mass)
       if count_grad_evals is not None:
         count_grad_evals[0] += B * unrolled_leapfrog_steps
       rho_prev = rho_s
@@ -261,10 +283,10 @@ def _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy
           break
         diff = (rho_s - Srho[kidx]).astype(f32)
         with np.errstate(invalid='ignore', over='ignore'):
-          ok = ok & (_dot(diff, Sm[kidx]) >= 0) & (_dot(diff, s_m) >= 0)
+          ok = ok & (_dot(diff, vel(Sm[kidx])) >= 0) & (_dot(diff, vel(s_m)) >= 0)
       w_i = write_instr[i]
       Sm[w_i] = s_m; Srho[w_i] = rho_prev                                # :859-869
-      en = _energy(s_lp, s_m)
+      en = _energy(s_lp, s_m, inv_mass)
       en = np.where(np.isnan(en), NEG_INF, en).astype(f32)               # :874-876
       with np.errstate(invalid='ignore', over='ignore'):
         dH = (en - H0).astype(f32)
@@ -309,7 +331,7 @@ def _nuts_one_step(target, x, lp, g, step_size, seed, max_tree_depth, max_energy
     end_g = np.stack([np.where(dcol, o_g, s_g), np.where(dcol, s_g, o_g)])
     rho = (rho + rho_s).astype(f32)                                      # :677-682
     with np.errstate(invalid='ignore', over='ignore'):
-      no_uturn = (_dot(rho, end_m[0]) >= 0) & (_dot(rho, end_m[1]) >= 0)  # :694-699
+      no_uturn = (_dot(rho, vel(end_m[0])) >= 0) & (_dot(rho, vel(end_m[1])) >= 0)  # :694-699
     accepted = swap | accepted
     cont = cont_f & no_uturn
     notdiv = nd

@@ -9,6 +9,7 @@ Everything that computes runs in hand-written sm_100a CUDA kernels behind the C 
 include/pb2.h (libpb2.so, loaded with ctypes).  There is no CPU fallback.
 """
 from probability_b200 import distribute
+from probability_b200 import experimental
 from probability_b200 import mcmc
 from probability_b200 import random
 from probability_b200 import targets

@@ -39,7 +39,7 @@ class RunCfg(C.Structure):
               ('max_energy_diff', C.c_float), ('unrolled_leapfrog_steps', C.c_int),
               ('num_results', C.c_int), ('num_burnin_steps', C.c_int),
               ('num_steps_between_results', C.c_int), ('step_kind', C.c_int),
-              ('explicit_step_seeds', C.c_int)]
+              ('explicit_step_seeds', C.c_int), ('d_momentum_scale', C.c_void_p)]
 
 
 TRACE_FIELDS = ['states', 'target_log_prob', 'grads_target_log_prob', 'log_accept_ratio',
@@ -106,6 +106,7 @@ def load():
         'pb2_da_init': ([vp, f32, i32, f32, f32, f32, f32, f32, i32, f32, f32, vp], i32),
         'pb2_da_partial': ([vp, vp, i32, vp], i32),
         'pb2_da_apply': ([vp, vp, i32, ll, vp, vp], i32),
+        'pb2_running_moments_update': ([vp, vp, ll, i32, vp], i32),
         'pb2_ess': ([vp, vp, i32, i32, i32, f32, i32, i32, i32, vp], i32),
         'pb2_rhat': ([vp, vp, i32, i32, i32, i32, vp], i32),
         'pb2_rowshard_logistic_grad': ([vp, vp, vp, i32, i32, i32, vp, i32, vp], i32),

@@ -352,6 +352,9 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
   p.max_depth = cfg->max_tree_depth;
   p.max_energy_diff = cfg->max_energy_diff;
   p.unrolled = cfg->unrolled_leapfrog_steps;
+  p.scale = cfg->d_momentum_scale;
+  if (p.scale && cfg->step_kind == PB2_STEP_PER_DIM)
+    return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_run: per-dimension step sizes together with a momentum scale");
   if (trace) {
     Trace& tr = p.tr;
     tr.states = trace->d_states;
@@ -388,6 +391,11 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
     p.lar_last = ctx->d_step_seq;
   }
 
+  // diagonal preconditioning: the kernels run on u = x / s with grad_u = s grad_x (converted back below)
+  if (p.scale) {
+    if (int rc = launch_scale_rows(ctx, d_x, (size_t)lay->B, p.D, p.scale, 1)) return rc;
+    if (int rc = launch_scale_rows(ctx, d_grad, (size_t)lay->B, p.D, p.scale, 0)) return rc;
+  }
   const int chunk_max = nuts ? std::max(1, (int)((64ull << 20) / (4ull * stride))) : (1 << 20);
   PrimIO io{};
   int t = 0;
@@ -429,6 +437,18 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
       if (int rc2 = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync(chunk)")) return rc2;
     t = t_end;
   }
+  if (p.scale) {   // back to the original coordinates: x = s u, grad_x = grad_u / s, momentum m_x = m_u / s
+    const size_t R = (size_t)cfg->num_results * (size_t)lay->B;
+    int rc = launch_scale_rows(ctx, d_x, (size_t)lay->B, p.D, p.scale, 0);
+    if (!rc) rc = launch_scale_rows(ctx, d_grad, (size_t)lay->B, p.D, p.scale, 1);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.states, R, p.D, p.scale, 0);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.grads, R, p.D, p.scale, 1);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.proposed_state, R, p.D, p.scale, 0);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.proposed_grads, R, p.D, p.scale, 1);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.initial_momentum, R, p.D, p.scale, 1);
+    if (!rc) rc = launch_scale_rows(ctx, p.tr.final_momentum, R, p.D, p.scale, 1);
+    if (rc) return rc;
+  }
   // `keys` (pageable host memory) must outlive the async copy
   return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync(run)");
 }
@@ -466,6 +486,14 @@ int pb2_da_apply(pb2_ctx* ctx, const float* d_partials, int n, long long B_globa
   if (!ctx || !d_partials || !d_state || n < 1 || B_global < 1) return set_error(ctx, PB2_ERR_INVALID, "pb2_da_apply: bad argument");
   cudaSetDevice(ctx->device);
   return launch_da_apply(ctx, d_partials, n, B_global, d_state, d_step_out, nullptr);
+}
+
+// ------------------------------------------------------------------ streaming moments
+int pb2_running_moments_update(pb2_ctx* ctx, const float* d_x, long long rows, int D, float* d_state) {
+  if (!ctx || !d_x || !d_state || rows < 0 || D < 1)
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_running_moments_update: bad argument");
+  cudaSetDevice(ctx->device);
+  return launch_running_moments(ctx, d_x, rows, D, d_state);
 }
 
 // ------------------------------------------------------------------ diagnostics

@@ -60,6 +60,7 @@ struct ChainParams {
   const uint32_t* sched;  // per-transition key schedule (see pb2_sched kernels)
   int sched_stride;       // uint32 words per transition
   float* ckpt_global;     // block groups: [gridDim.x][2*max_depth*E*G]
+  const float* scale;     // (nullable, [D]) diagonal preconditioning: the kernels run on u = x / scale (pb2_targets.cuh ScaledT)
   Trace tr;
 };
 

@@ -187,16 +187,26 @@ static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, C
   return set_error(ctx, PB2_ERR_INVALID, "bad mode");
 }
 
+// the same launch with the target wrapped for diagonal preconditioning when the run carries a scale
+template <class Grp, int E, class Tgt, int MAXT = 512>
+static int launch_maybe_scaled(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
+  if (!p.scale) return launch_mode<Grp, E, Tgt, MAXT>(ctx, tp, mode, p, io);
+  using S = ScaledT<Grp, E, Tgt>;
+  typename S::Params sp{tp, p.scale, p.D};
+  return launch_mode<Grp, E, S, MAXT>(ctx, sp, mode, p, io);
+}
+
 int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io) {
   const int D = tgt->dim;
   if (tile_path_supported(ctx, tgt, mode, p)) return launch_tile_chain(ctx, tgt, mode, p);
   switch (tgt->kind) {
     case PB2_TARGET_EIGHT_SCHOOLS: {
       EightSchoolsParams tp{tgt->d_a, tgt->d_b, tgt->n_rows};
-      return launch_mode<WarpG, 1, EightSchoolsT<WarpG, 1>>(ctx, tp, mode, p, io);
+      return launch_maybe_scaled<WarpG, 1, EightSchoolsT<WarpG, 1>>(ctx, tp, mode, p, io);
     }
     case PB2_TARGET_DENSE_GAUSSIAN: {
       DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, D};
+      tp.scale = p.scale;
       if (D <= 32) return launch_mode<WarpG, 1, DenseGaussianT<WarpG, 1>>(ctx, tp, mode, p, io);
       if (D <= 128) {
         // experiment kept for A/B profiling (PB2_DENSE_VARIANT=2): two chains per warp, 16 lanes x 8 elements,
@@ -209,14 +219,14 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
     }
     case PB2_TARGET_LOGISTIC: {
       LogisticParams tp{tgt->d_a, tgt->d_b, tgt->n_rows, D};
-      if (D <= 8) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 8>>(ctx, tp, mode, p, io);
-      if (D <= 25) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 25>>(ctx, tp, mode, p, io);
-      if (D <= 32) return launch_mode<WarpG, 1, LogisticT<WarpG, 1, 32>>(ctx, tp, mode, p, io);
+      if (D <= 8) return launch_maybe_scaled<WarpG, 1, LogisticT<WarpG, 1, 8>>(ctx, tp, mode, p, io);
+      if (D <= 25) return launch_maybe_scaled<WarpG, 1, LogisticT<WarpG, 1, 25>>(ctx, tp, mode, p, io);
+      if (D <= 32) return launch_maybe_scaled<WarpG, 1, LogisticT<WarpG, 1, 32>>(ctx, tp, mode, p, io);
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "shared-memory logistic: D > 32 (use the row-sharded path)");
     }
     case PB2_TARGET_STOCH_VOL: {
       StochVolParams tp{tgt->d_a, tgt->n_rows};
-      if (D <= 5 * 512) return launch_mode<BlockG<16>, 5, StochVolT<BlockG<16>, 5>>(ctx, tp, mode, p, io);
+      if (D <= 5 * 512) return launch_maybe_scaled<BlockG<16>, 5, StochVolT<BlockG<16>, 5>>(ctx, tp, mode, p, io);
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
     }
   }

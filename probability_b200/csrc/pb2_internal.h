@@ -97,6 +97,8 @@ int launch_da_partial(pb2_ctx* ctx, const float* d_lar, int B, float* d_partial)
 int launch_da_apply(pb2_ctx* ctx, const float* d_partials, int n, long long B_global, float* d_state,
                     float* d_step_out, float* d_step_seq_next);
 int launch_fill_step_seq(pb2_ctx* ctx, float* d_seq, const float* d_step, int n);
+int launch_scale_rows(pb2_ctx* ctx, float* d_a, size_t rows, int D, const float* d_s, int div);
+int launch_running_moments(pb2_ctx* ctx, const float* d_x, long long rows, int D, float* d_state);
 int launch_rng_fill(pb2_ctx* ctx, Key key, Key key_hi, long long n, int layout, int what, float lo, float hi,
                     int ilo, int ihi, void* out);
 int launch_ess(pb2_ctx* ctx, const float* d_states, int N, int B, int D, float thr, int use_thr, int max_lag,

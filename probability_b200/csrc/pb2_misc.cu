@@ -1,6 +1,7 @@
 // Small kernels around the chain kernels: key-schedule expansion, bulk RNG draws,
 // dual-averaging step-size adaptation, ESS and R-hat cross-chain reductions.
 #include <cmath>
+#include <algorithm>
 #include "pb2_internal.h"
 
 namespace pb2 {
@@ -207,6 +208,89 @@ int launch_fill_step_seq(pb2_ctx* ctx, float* d_seq, const float* d_step, int n)
   fill_step_seq_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_seq, d_step, n);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "fill_step_seq_kernel");
+}
+
+// ---------------------------------------------------------------- diagonal preconditioning / streaming moments
+// a[r, d] *= s[d]  (div: /= s[d]) over a [rows, D] array: x <-> u = x / s, grad_x <-> grad_u = s grad_x
+__global__ void scale_rows_kernel(float* a, size_t n, int D, const float* s, int div) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sc = s[i % D];
+  a[i] = div ? a[i] / sc : a[i] * sc;
+}
+
+int launch_scale_rows(pb2_ctx* ctx, float* d_a, size_t rows, int D, const float* d_s, int div) {
+  const size_t n = rows * (size_t)D;
+  if (!d_a || n == 0) return PB2_OK;
+  scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_a, n, D, d_s, div);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "scale_rows_kernel");
+}
+
+// Running mean / sum of squared deviations per dimension over the rows of x [rows, D] (Welford within a row segment,
+// Chan's pairwise merge across segments and into the running state, both in a fixed order: deterministic).
+// experimental/stats/sample_stats.py RunningVariance.update: every row is one new observation.
+__global__ void moments_partial_kernel(const float* __restrict__ x, long long rows, int D, long long rows_per_seg,
+                                       float* __restrict__ part /*[nseg][3][D]*/) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_seg;
+  const long long r1 = min(rows, r0 + rows_per_seg);
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float v = x[(size_t)r * D + d];
+    n += 1.f;
+    const float delta = v - mean;
+    mean += delta / n;
+    m2 = fmaf(delta, v - mean, m2);
+  }
+  float* o = part + (size_t)blockIdx.y * 3 * D;
+  o[d] = n; o[D + d] = mean; o[2 * D + d] = m2;
+}
+
+__global__ void moments_merge_kernel(const float* __restrict__ part, int nseg, int D, float* __restrict__ state) {
+  const float n0 = state[0];   // the count is shared by all dimensions: read by everybody before thread 0 rewrites it
+  float n_out = n0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float n = n0, mean = state[1 + d], m2 = state[1 + D + d];
+    for (int s = 0; s < nseg; ++s) {
+      const float* o = part + (size_t)s * 3 * D;
+      const float nb = o[d], mb = o[D + d], m2b = o[2 * D + d];
+      if (nb > 0.f) {
+        const float nt = n + nb, delta = mb - mean;
+        mean += delta * (nb / nt);
+        m2 += m2b + delta * delta * (n * nb / nt);
+        n = nt;
+      }
+    }
+    state[1 + d] = mean;
+    state[1 + D + d] = m2;
+    n_out = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) state[0] = n_out;
+}
+
+int launch_running_moments(pb2_ctx* ctx, const float* d_x, long long rows, int D, float* d_state) {
+  if (rows <= 0) return PB2_OK;
+  int nseg = (int)std::min<long long>(rows, 4 * (long long)ctx->num_sms);
+  const long long rps = (rows + nseg - 1) / nseg;
+  nseg = (int)((rows + rps - 1) / rps);
+  const size_t need = sizeof(float) * 3 * (size_t)D * nseg;
+  if (need > ctx->sched_bytes) {
+    if (ctx->d_sched) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_sched); }
+    ctx->d_sched = nullptr;
+    ctx->sched_bytes = 0;
+    if (int rc = check_cuda(ctx, cudaMalloc((void**)&ctx->d_sched, need), "cudaMalloc(moments partials)")) return rc;
+    ctx->sched_bytes = need;
+  }
+  float* part = reinterpret_cast<float*>(ctx->d_sched);
+  const int bt = 128;
+  moments_partial_kernel<<<dim3((D + bt - 1) / bt, nseg), bt, 0, ctx->stream>>>(d_x, rows, D, rps, part);
+  // one block merges: the count lives in state[0] and is read by every dimension before it is rewritten
+  moments_merge_kernel<<<1, 1024, 0, ctx->stream>>>(part, nseg, D, d_state);
+  ctx->launches += 2;
+  return check_cuda(ctx, cudaGetLastError(), "running moments kernels");
 }
 
 // ---------------------------------------------------------------- diagnostics

@@ -81,7 +81,11 @@ struct DenseGaussianParams {
   const float* loc;  // [D] device
   float lognorm;
   int D;
+  // (nullable) per-dimension scale s of a diagonally preconditioned run: the kernels then sample u = x / s, i.e. the
+  // Gaussian with precision diag(s) P diag(s) and location loc / s (see ScaledT below)
+  const float* scale = nullptr;
 };
+__device__ __forceinline__ float dense_scale_at(const DenseGaussianParams& p, int d) { return p.scale ? p.scale[d] : 1.f; }
 
 template <class Grp, int E>
 struct DenseGaussianT {
@@ -99,7 +103,7 @@ struct DenseGaussianT {
   __device__ void init_cta(const Params& p, float* cta) {
     for (int i = threadIdx.x; i < p.D * DP; i += blockDim.x) {
       int r = i / DP, c = i - r * DP;
-      cta[i] = (c < p.D) ? p.P[r * p.D + c] : 0.f;
+      cta[i] = (c < p.D) ? (dense_scale_at(p, r) * p.P[r * p.D + c]) * dense_scale_at(p, c) : 0.f;
     }
   }
   __device__ void init_group(const Params& p, Grp& grp, float* cta, float* grp_smem) {
@@ -110,7 +114,7 @@ struct DenseGaussianT {
 #pragma unroll
     for (int j = 0; j < E; ++j) {
       int d = grp.lane * E + j;
-      loc[j] = d < D ? p.loc[d] : 0.f;
+      loc[j] = d < D ? p.loc[d] / dense_scale_at(p, d) : 0.f;
     }
   }
   __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
@@ -177,6 +181,46 @@ struct DenseGaussianT {
     }
     grp.sync();  // xbuf is rewritten by the next call
     return fmaf(0.5f, grp.sum(part), lognorm);
+  }
+};
+
+// --------------------------------------------------------------------------
+// Diagonal preconditioning as a change of variables: HMC / NUTS on x with the diagonal mass matrix M = diag(1 / s^2)
+// (momentum ~ N(0, M), velocity s^2 m, kinetic energy 1/2 sum s^2 m^2, U-turn test <rho, velocity>:
+// tfp/experimental/mcmc/preconditioned_hmc.py, preconditioned_nuts.py:694-705,964-1030,
+// diagonal_mass_matrix_adaptation.py:73) is, step for step, identity-mass HMC / NUTS on u = x / s with momentum s m:
+// the same standard-normal draw z is the momentum there, x moves by eps s z in both, and <rho_u, m_u> = <rho_x, s^2 m_x>.
+// So the transition code stays untouched and any target gets preconditioning from this wrapper: lp(u) = lp_x(s u),
+// grad_u = s grad_x.  (The dense Gaussian folds s into its precision matrix instead, so the tensor-core kernels apply.)
+template <class Grp, int E, class Tgt>
+struct ScaledT {
+  struct Params {
+    typename Tgt::Params base;
+    const float* scale;  // [D] device
+    int D;
+  };
+  static constexpr bool kCkptInSmem = Tgt::kCkptInSmem;
+  Tgt base;
+  float sc[E];
+  static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
+  static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
+  __device__ void init_cta(const Params& p, float* cta) { base.init_cta(p.base, cta); }
+  __device__ void init_group(const Params& p, Grp& grp, float* cta, float* gs) {
+    base.init_group(p.base, grp, cta, gs);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int d = grp.lane * E + j;
+      sc[j] = d < p.D ? p.scale[d] : 1.f;
+    }
+  }
+  __device__ float logp_grad(Grp& grp, const float (&u)[E], float (&g)[E]) {
+    float x[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = sc[j] * u[j];
+    const float lp = base.logp_grad(grp, x, g);
+#pragma unroll
+    for (int j = 0; j < E; ++j) g[j] = sc[j] * g[j];
+    return lp;
   }
 };
 

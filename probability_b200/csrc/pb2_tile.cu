@@ -54,7 +54,7 @@ tile_hmc_kernel(const ChainParams p, const DenseGaussianParams tp) {
   extern __shared__ __align__(128) unsigned char planes[];
   __shared__ Shared sh;
   Ctx cx;
-  cx.init(&sh, planes, tp.P, tp.loc, tp.D);
+  cx.init(&sh, planes, tp.P, tp.loc, tp.D, tp.scale);
   const int D = tp.D;
   const int ntiles = (p.B + kM - 1) / kM;
   for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
@@ -164,6 +164,7 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
 
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p) {
   DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, tgt->dim};
+  tp.scale = p.scale;
   const size_t smem = 2 * (size_t)kPlaneBytes;
   const int ntiles = (p.B + kM - 1) / kM;
   const int grid = std::min(ntiles, ctx->num_sms);

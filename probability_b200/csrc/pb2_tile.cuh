@@ -139,7 +139,7 @@ struct Ctx {
   int cl, slice, parity;
 
   // One-time setup: TMEM allocation, mbarrier, P hi/lo planes (canonical layout), loc.
-  __device__ void init(Shared* sh_, unsigned char* planes, const float* P, const float* loc, int D) {
+  __device__ void init(Shared* sh_, unsigned char* planes, const float* P, const float* loc, int D, const float* scale = nullptr) {
     sh = sh_;
     const int tid = threadIdx.x, warp = tid >> 5;
     cl = 32 * (warp & 3) + (tid & 31);
@@ -160,13 +160,15 @@ struct Ctx {
     unsigned char* b_lo = planes + kPlaneBytes;
     for (int i = tid; i < kNP * kKP; i += kThreads) {
       const int n = i / kKP, k = i - n * kKP;
-      const float v = (n < D && k < D) ? P[n * D + k] : 0.f;   // B[n][k] = P[k][n] = P[n][k]
+      // B[n][k] = P[k][n] = P[n][k]; a diagonally preconditioned run samples u = x / s: precision diag(s) P diag(s)
+      float v = (n < D && k < D) ? P[n * D + k] : 0.f;
+      if (scale && n < D && k < D) v = (scale[n] * v) * scale[k];
       const float hi = tf32_rna(v);
       const int off = b_plane_offset(n, k);
       *reinterpret_cast<float*>(b_hi + off) = hi;
       *reinterpret_cast<float*>(b_lo + off) = tf32_rna(v - hi);
     }
-    for (int i = tid; i < kKP; i += kThreads) sh->loc[i] = i < D ? loc[i] : 0.f;
+    for (int i = tid; i < kKP; i += kThreads) sh->loc[i] = i < D ? (scale ? loc[i] / scale[i] : loc[i]) : 0.f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (UMMA)
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

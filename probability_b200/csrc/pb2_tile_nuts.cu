@@ -283,7 +283,7 @@ tile_nuts_kernel(const ChainParams p, const DenseGaussianParams tp, float* __res
   __shared__ float lu[4][kM];   // log1p(-u) of the multinomial draws of 4 consecutive leaves
   Ctx cx;
   float* const dyn = reinterpret_cast<float*>(planes + 2 * kPlaneBytes);
-  cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D);
+  cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D, tp.scale);
   Prof pf;
   pf.init();
   const int D = tp.D;
@@ -509,7 +509,7 @@ tile_nuts_async_kernel(const ChainParams p, const DenseGaussianParams tp, float*
   __shared__ int st_lane[kM], st_c[kM], st_t[kM];
   Ctx cx;
   float* const dyn = reinterpret_cast<float*>(planes + 2 * kPlaneBytes);
-  cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D);
+  cx.init(&sh, planes, dyn + 2 * kVS, tp.P, tp.loc, tp.D, tp.scale);
   Prof pf;
   pf.init();
   const int D = tp.D;
@@ -854,6 +854,7 @@ static int ensure_scratch(pb2_ctx* ctx, size_t need, const char* what) {
 
 int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p) {
   DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, tgt->dim};
+  tp.scale = p.scale;
   // P hi/lo planes + the previous leaf's checkpoint (momentum, rho) + the gradient exchange buffer
   const size_t smem = 2 * (size_t)kPlaneBytes + (2 * kVS + kXbufFloats) * sizeof(float);
   const int ntiles = (p.B + kM - 1) / kM;

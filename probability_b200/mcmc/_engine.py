@@ -128,7 +128,8 @@ ChainShard = collections.namedtuple('ChainShard', ['chain_offset', 'num_chains_g
 def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_burnin_steps=0,
         num_steps_between_results=0, seed=None, step_seeds=None, num_leapfrog_steps=1,
         max_tree_depth=10, max_energy_diff=1000.0, unrolled_leapfrog_steps=1, want=(),
-        da_state=None, shard=None, leapfrog_total=None, layout=None, da_over_ranks=False):
+        da_state=None, shard=None, leapfrog_total=None, layout=None, da_over_ranks=False,
+        momentum_scale=None):
   """Calls pb2_run.  x, lp, g, step are updated IN PLACE (pass clones to keep inputs).
   Returns (trace dict of tensors with leading R, final pass-along seed, step seeds)."""
   import torch
@@ -151,7 +152,8 @@ def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_bur
                     unrolled_leapfrog_steps=int(unrolled_leapfrog_steps), num_results=int(num_results),
                     num_burnin_steps=int(num_burnin_steps),
                     num_steps_between_results=int(num_steps_between_results), step_kind=int(step_kind),
-                    explicit_step_seeds=0 if step_seeds is None else 1)
+                    explicit_step_seeds=0 if step_seeds is None else 1,
+                    d_momentum_scale=None if momentum_scale is None else momentum_scale.data_ptr())
   n_steps = int(num_burnin_steps) + 1 + (int(num_results) - 1) * (1 + int(num_steps_between_results))
   if step_seeds is None:
     h_seed = np.ascontiguousarray(np.asarray(seed, np.uint32).reshape(2)).copy()

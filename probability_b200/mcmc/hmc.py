@@ -231,6 +231,13 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
   def _lockstep(self):
     return getattr(self._target, 'is_lockstep', False)
 
+  @staticmethod
+  def _momentum_scale(accepted_results, shapes, device):
+    """sqrt of the diagonal inverse mass matrix ([D] CUDA tensor) when the results carry a momentum distribution
+    (PreconditionedHamiltonianMonteCarlo), else None."""
+    md = getattr(accepted_results, 'momentum_distribution', None)
+    return None if md is None else md.scale_vector(shapes, device)
+
   def one_step(self, current_state, previous_kernel_results, seed=None):
     pkr = previous_kernel_results
     if self._lockstep:   # MetropolisHastings(UncalibratedHMC) over the lock-step leapfrog
@@ -248,7 +255,7 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
             'proposed_grads', 'log_acceptance_correction', 'initial_momentum', 'final_momentum')
     out, _, _ = _engine.run(self._target, x, lp, g, step, step_kind, shapes, kind=_lib.KERNEL_HMC,
                             num_results=1, step_seeds=seed[None, :], num_leapfrog_steps=L, want=want,
-                            shard=self.chain_shard)
+                            shard=self.chain_shard, momentum_scale=self._momentum_scale(acc, shapes, x.device))
     is_acc = out['is_accepted'][0]
     proposal_seed = pb_random.split_seed(seed)[0]
     proposed = acc._replace(
@@ -299,7 +306,8 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
         self._target, x, lp, g, step, step_kind, shapes, kind=_lib.KERNEL_HMC, num_results=num_results,
         num_burnin_steps=num_burnin_steps, num_steps_between_results=num_steps_between_results, seed=seed,
         num_leapfrog_steps=L, want=tuple(want), da_state=da_state, shard=self.chain_shard,
-        leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks)
+        leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks,
+        momentum_scale=self._momentum_scale(acc, shapes, x.device))
     traced = {}
     for p in paths:
       v = out[self._FUSED_FIELDS[p]] if self._FUSED_FIELDS[p] in out else None

@@ -17,6 +17,24 @@ NUTSKernelResults = collections.namedtuple(
      'is_accepted', 'reach_max_depth', 'has_divergence', 'energy', 'seed'])
 
 
+# experimental/mcmc/preconditioned_nuts.py:86-131: the same results plus the momentum distribution
+PreconditionedNUTSKernelResults = collections.namedtuple(
+    'PreconditionedNUTSKernelResults', NUTSKernelResults._fields + ('momentum_distribution',))
+
+
+def _results_like(pkr, **fields):
+  """NUTS results of the type of `pkr` (the preconditioned kernel carries its momentum distribution along)."""
+  if hasattr(pkr, 'momentum_distribution'):
+    return PreconditionedNUTSKernelResults(momentum_distribution=pkr.momentum_distribution, **fields)
+  return NUTSKernelResults(**fields)
+
+
+def momentum_scale_of(results, shapes, device):
+  """sqrt of the diagonal inverse mass matrix as a [D] CUDA tensor, or None for the identity."""
+  md = getattr(results, 'momentum_distribution', None)
+  return None if md is None else md.scale_vector(shapes, device)
+
+
 def build_tree_uturn_instruction(max_depth, init_memory=0):
   """(left, right) leaf index pairs of every balanced subtree (nuts.py:1013-1028)."""
   pairs = set()
@@ -133,8 +151,9 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
         step_seeds=seed[None, :], max_tree_depth=self.max_tree_depth, max_energy_diff=self.max_energy_diff,
         unrolled_leapfrog_steps=self.unrolled_leapfrog_steps,
         want=('log_accept_ratio', 'leapfrogs_taken', 'is_accepted', 'reach_max_depth', 'has_divergence',
-              'energy'), shard=self.chain_shard)
-    results = NUTSKernelResults(
+              'energy'), shard=self.chain_shard, momentum_scale=momentum_scale_of(pkr, shapes, x.device))
+    results = _results_like(
+        pkr,
         target_log_prob=lp, grads_target_log_prob=_engine.unflatten(g, shapes, True),
         step_size=pkr.step_size, log_accept_ratio=out['log_accept_ratio'][0],
         leapfrogs_taken=out['leapfrogs_taken'][0], is_accepted=out['is_accepted'][0],
@@ -165,7 +184,8 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
         num_burnin_steps=num_burnin_steps, num_steps_between_results=num_steps_between_results, seed=seed,
         max_tree_depth=self.max_tree_depth, max_energy_diff=self.max_energy_diff,
         unrolled_leapfrog_steps=self.unrolled_leapfrog_steps, want=tuple(want), da_state=da_state,
-        shard=self.chain_shard, leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks)
+        shard=self.chain_shard, leapfrog_total=leapfrog_total, da_over_ranks=da_over_ranks,
+        momentum_scale=momentum_scale_of(pkr, shapes, x.device))
     traced = {}
     for p in paths:
       v = out.get(self._FUSED_FIELDS[p])
@@ -175,7 +195,8 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
     new_step = pkr.step_size
     if step_kind == _lib.STEP_SCALAR and da_state is not None:
       new_step = step.reshape(()).clone()
-    final = NUTSKernelResults(
+    final = _results_like(
+        pkr,
         target_log_prob=lp, grads_target_log_prob=_engine.unflatten(g, shapes, True), step_size=new_step,
         log_accept_ratio=out['log_accept_ratio'][-1], leapfrogs_taken=out['leapfrogs_taken'][-1],
         is_accepted=out['is_accepted'][-1], reach_max_depth=out['reach_max_depth'][-1],
