@@ -53,6 +53,13 @@ extern "C" {
 #define PB2_TARGET_DENSE_GAUSSIAN 1
 #define PB2_TARGET_LOGISTIC 2
 #define PB2_TARGET_STOCH_VOL 3
+#define PB2_TARGET_STOCH_VOL_CONSTRAINED 4 /* the same model in its own coordinates [persistence, mean, scale, z] */
+
+/* elementwise event-space bijectors (one per state dimension), tfp/bijectors/{identity,exp,softplus,sigmoid}.py */
+#define PB2_BIJECTOR_IDENTITY 0
+#define PB2_BIJECTOR_EXP 1
+#define PB2_BIJECTOR_SOFTPLUS 2
+#define PB2_BIJECTOR_SIGMOID 3 /* Sigmoid(low, high) */
 
 /* transition kinds */
 #define PB2_KERNEL_HMC 0
@@ -121,6 +128,11 @@ typedef struct {
 int pb2_logp_grad(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x /*[B,D]*/,
                   float* d_logp /*[B]*/, float* d_grad /*[B,D]*/);
 
+/* pb2_logp_grad of the target composed with event-space bijectors (see pb2_run_cfg.d_bijector_*): d_x is the
+ * unconstrained state, logp includes the forward log-det-Jacobian (transformed_kernel.py:86-140). */
+int pb2_logp_grad_transformed(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, const int32_t* d_bijector_kind,
+                              const float* d_bijector_low, const float* d_bijector_high, float* d_logp, float* d_grad);
+
 int pb2_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, const float* d_x,
                  const float* d_logp, const float* d_grad, const float* d_step, int step_kind,
                  int num_steps, float* d_m_out, float* d_x_out, float* d_logp_out, float* d_grad_out);
@@ -157,6 +169,13 @@ typedef struct {
                                builds (experimental/mcmc/preconditioned_hmc.py, preconditioned_nuts.py:169,
                                diagonal_mass_matrix_adaptation.py:73).  States, gradients and momenta cross the ABI in
                                the ORIGINAL coordinates; inside, the kernels run on u = x / s (pb2_targets.cuh). */
+  /* NULL, or [D] device arrays: event-space bijectors of a TransformedTransitionKernel (mcmc/transformed_kernel.py:
+   * 86-140,369-419).  The chain state d_x is then the UNCONSTRAINED state, the target is evaluated at
+   * forward(state) and the forward log-det-Jacobian and its derivative are added (PB2_BIJECTOR_* per dimension,
+   * low / high read for PB2_BIJECTOR_SIGMOID only). */
+  const int32_t* d_bijector_kind;
+  const float* d_bijector_low;
+  const float* d_bijector_high;
 } pb2_run_cfg;
 
 /* Nullable per-result outputs; leading dimension R = num_results.

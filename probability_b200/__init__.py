@@ -8,6 +8,7 @@
 Everything that computes runs in hand-written sm_100a CUDA kernels behind the C ABI in
 include/pb2.h (libpb2.so, loaded with ctypes).  There is no CPU fallback.
 """
+from probability_b200 import bijectors
 from probability_b200 import distribute
 from probability_b200 import experimental
 from probability_b200 import mcmc

@@ -17,6 +17,7 @@ PB2_OK = 0
 LAYOUT_PARTITIONABLE = 0
 LAYOUT_ORIGINAL = 1
 TARGET_EIGHT_SCHOOLS, TARGET_DENSE_GAUSSIAN, TARGET_LOGISTIC, TARGET_STOCH_VOL = 0, 1, 2, 3
+TARGET_STOCH_VOL_CONSTRAINED = 4
 KERNEL_HMC, KERNEL_NUTS = 0, 1
 STEP_SCALAR, STEP_PER_DIM, STEP_PER_CHAIN = 0, 1, 2
 
@@ -39,7 +40,8 @@ class RunCfg(C.Structure):
               ('max_energy_diff', C.c_float), ('unrolled_leapfrog_steps', C.c_int),
               ('num_results', C.c_int), ('num_burnin_steps', C.c_int),
               ('num_steps_between_results', C.c_int), ('step_kind', C.c_int),
-              ('explicit_step_seeds', C.c_int), ('d_momentum_scale', C.c_void_p)]
+              ('explicit_step_seeds', C.c_int), ('d_momentum_scale', C.c_void_p),
+              ('d_bijector_kind', C.c_void_p), ('d_bijector_low', C.c_void_p), ('d_bijector_high', C.c_void_p)]
 
 
 TRACE_FIELDS = ['states', 'target_log_prob', 'grads_target_log_prob', 'log_accept_ratio',
@@ -98,6 +100,7 @@ def load():
         'pb2_rng_normal': ([vp, c_u32p, ll, i32, vp], i32),
         'pb2_rng_randint': ([vp, c_u32p, ll, i32, i32, i32, vp], i32),
         'pb2_logp_grad': ([vp, vp, i32, vp, vp, vp], i32),
+        'pb2_logp_grad_transformed': ([vp, vp, i32, vp, vp, vp, vp, vp, vp], i32),
         'pb2_dense_logp_grad_tc': ([vp, vp, i32, vp, vp, vp], i32),
         'pb2_logistic_logp_grad_tc': ([vp, vp, i32, vp, vp, vp], i32),
         'pb2_leapfrog': ([vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp], i32),

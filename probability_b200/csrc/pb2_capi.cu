@@ -140,6 +140,7 @@ int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* d, pb2_target** out) 
       nb = d->n_rows;
       break;
     case PB2_TARGET_STOCH_VOL:
+    case PB2_TARGET_STOCH_VOL_CONSTRAINED:
       if (d->n_rows < 1 || d->dim != d->n_rows + 3 || d->dim > 2560)
         return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: need dim == T + 3 <= 2560");
       na = d->n_rows;
@@ -255,6 +256,24 @@ int pb2_logp_grad(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, 
   return launch_chain(ctx, tgt, kModeLogpGrad, p, io);
 }
 
+int pb2_logp_grad_transformed(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_x, const int32_t* d_kind,
+                              const float* d_lo, const float* d_hi, float* d_logp, float* d_grad) {
+  if (!ctx || !tgt || !d_x || !d_logp || !d_grad || !d_kind || !d_lo || !d_hi || B < 0)
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_logp_grad_transformed: bad argument");
+  if (B == 0) return PB2_OK;
+  cudaSetDevice(ctx->device);
+  ChainParams p;
+  base_params(p, tgt, B);
+  p.bij_kind = d_kind;
+  p.bij_lo = d_lo;
+  p.bij_hi = d_hi;
+  PrimIO io{};
+  io.x_in = d_x;
+  io.lp_out = d_logp;
+  io.g_out = d_grad;
+  return launch_chain(ctx, tgt, kModeLogpGrad, p, io);
+}
+
 int pb2_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, const float* d_x, const float* d_logp,
                  const float* d_grad, const float* d_step, int step_kind, int num_steps, float* d_m_out,
                  float* d_x_out, float* d_logp_out, float* d_grad_out) {
@@ -353,6 +372,11 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
   p.max_energy_diff = cfg->max_energy_diff;
   p.unrolled = cfg->unrolled_leapfrog_steps;
   p.scale = cfg->d_momentum_scale;
+  p.bij_kind = cfg->d_bijector_kind;
+  p.bij_lo = cfg->d_bijector_low;
+  p.bij_hi = cfg->d_bijector_high;
+  if (p.bij_kind && (!p.bij_lo || !p.bij_hi))
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_run: d_bijector_kind needs d_bijector_low and d_bijector_high");
   if (p.scale && cfg->step_kind == PB2_STEP_PER_DIM)
     return set_error(ctx, PB2_ERR_UNSUPPORTED, "pb2_run: per-dimension step sizes together with a momentum scale");
   if (trace) {

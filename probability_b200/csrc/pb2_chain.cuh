@@ -61,6 +61,9 @@ struct ChainParams {
   int sched_stride;       // uint32 words per transition
   float* ckpt_global;     // block groups: [gridDim.x][2*max_depth*E*G]
   const float* scale;     // (nullable, [D]) diagonal preconditioning: the kernels run on u = x / scale (pb2_targets.cuh ScaledT)
+  const int* bij_kind;    // (nullable, [D]) per-dimension event-space bijectors: the chains live in the unconstrained
+  const float* bij_lo;    //   space of a TransformedTransitionKernel (pb2_targets.cuh TransformedT)
+  const float* bij_hi;
   Trace tr;
 };
 

@@ -190,6 +190,11 @@ static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, C
 // the same launch with the target wrapped for diagonal preconditioning when the run carries a scale
 template <class Grp, int E, class Tgt, int MAXT = 512>
 static int launch_maybe_scaled(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
+  if (p.bij_kind) {
+    using T = TransformedT<Grp, E, Tgt>;
+    typename T::Params bp{tp, BijectorSpec{p.bij_kind, p.bij_lo, p.bij_hi}, p.scale, p.D};
+    return launch_mode<Grp, E, T, MAXT>(ctx, bp, mode, p, io);
+  }
   if (!p.scale) return launch_mode<Grp, E, Tgt, MAXT>(ctx, tp, mode, p, io);
   using S = ScaledT<Grp, E, Tgt>;
   typename S::Params sp{tp, p.scale, p.D};
@@ -206,6 +211,10 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
     }
     case PB2_TARGET_DENSE_GAUSSIAN: {
       DenseGaussianParams tp{tgt->d_a, tgt->d_b, tgt->scalar, D};
+      if (p.bij_kind) {   // bijectors: the generic wrapper (which also applies the scale) around the plain target
+        if (D <= 32) return launch_maybe_scaled<WarpG, 1, DenseGaussianT<WarpG, 1>>(ctx, tp, mode, p, io);
+        if (D <= 128) return launch_maybe_scaled<WarpG, 4, DenseGaussianT<WarpG, 4>>(ctx, tp, mode, p, io);
+      }
       tp.scale = p.scale;
       if (D <= 32) return launch_mode<WarpG, 1, DenseGaussianT<WarpG, 1>>(ctx, tp, mode, p, io);
       if (D <= 128) {
@@ -223,6 +232,11 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
       if (D <= 25) return launch_maybe_scaled<WarpG, 1, LogisticT<WarpG, 1, 25>>(ctx, tp, mode, p, io);
       if (D <= 32) return launch_maybe_scaled<WarpG, 1, LogisticT<WarpG, 1, 32>>(ctx, tp, mode, p, io);
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "shared-memory logistic: D > 32 (use the row-sharded path)");
+    }
+    case PB2_TARGET_STOCH_VOL_CONSTRAINED: {
+      StochVolParams tp{tgt->d_a, tgt->n_rows};
+      if (D <= 5 * 512) return launch_maybe_scaled<BlockG<16>, 5, StochVolT<BlockG<16>, 5, false>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
     }
     case PB2_TARGET_STOCH_VOL: {
       StochVolParams tp{tgt->d_a, tgt->n_rows};

@@ -225,6 +225,75 @@ struct ScaledT {
 };
 
 // --------------------------------------------------------------------------
+// TransformedTransitionKernel's target (tfp/mcmc/transformed_kernel.py:86-140,165,369-419): the chain lives in the
+// unconstrained u, the wrapped target sees x = b(u), and the density carries the forward log-det-Jacobian:
+//   lp(u) = lp_x(b(u)) + sum_d fldj_d(u_d),   grad_u = grad_x b'(u) + fldj'(u)
+// with one elementwise bijector per dimension (bijectors/{identity,exp,softplus,sigmoid}.py):
+//   Identity        b = u                      fldj = 0
+//   Exp             b = e^u                    fldj = u
+//   Softplus        b = log(1 + e^u)           fldj = -softplus(-u)
+//   Sigmoid(lo,hi)  b = lo + (hi - lo) s(u)    fldj = log(hi - lo) - softplus(-u) - softplus(u)
+// An optional diagonal preconditioning scale is applied first (u = scale * w, see ScaledT).
+enum { kBijIdentity = 0, kBijExp = 1, kBijSoftplus = 2, kBijSigmoid = 3 };
+struct BijectorSpec {
+  const int* kind;     // [D] device
+  const float* lo;     // [D] device (Sigmoid)
+  const float* hi;
+};
+
+template <class Grp, int E, class Tgt>
+struct TransformedT {
+  struct Params {
+    typename Tgt::Params base;
+    BijectorSpec bij;
+    const float* scale;  // nullable
+    int D;
+  };
+  static constexpr bool kCkptInSmem = Tgt::kCkptInSmem;
+  Tgt base;
+  float sc[E], lo[E], hi[E];
+  int kind[E];
+  static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
+  static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
+  __device__ void init_cta(const Params& p, float* cta) { base.init_cta(p.base, cta); }
+  __device__ void init_group(const Params& p, Grp& grp, float* cta, float* gs) {
+    base.init_group(p.base, grp, cta, gs);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int d = grp.lane * E + j;
+      const bool in = d < p.D;
+      sc[j] = (in && p.scale) ? p.scale[d] : 1.f;
+      kind[j] = in ? p.bij.kind[d] : kBijIdentity;
+      lo[j] = in ? p.bij.lo[d] : 0.f;
+      hi[j] = in ? p.bij.hi[d] : 1.f;
+    }
+  }
+  __device__ float logp_grad(Grp& grp, const float (&w)[E], float (&g)[E]) {
+    float x[E], db[E], dj[E];
+    float fldj = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const float u = sc[j] * w[j];
+      float b = u, d1 = 1.f, d2 = 0.f, lj = 0.f;
+      if (kind[j] == kBijExp) {
+        b = expf(u); d1 = b; d2 = 1.f; lj = u;
+      } else if (kind[j] == kBijSoftplus) {
+        b = softplusf(u); d1 = sigmoidf(u); d2 = sigmoidf(-u); lj = -softplusf(-u);
+      } else if (kind[j] == kBijSigmoid) {
+        const float s = sigmoidf(u), sm = sigmoidf(-u), w_ = hi[j] - lo[j];
+        b = lo[j] + w_ * s; d1 = w_ * s * sm; d2 = sm - s; lj = logf(w_) - softplusf(-u) - softplusf(u);
+      }
+      x[j] = b; db[j] = d1; dj[j] = d2;
+      fldj += lj;
+    }
+    const float lp = base.logp_grad(grp, x, g);
+#pragma unroll
+    for (int j = 0; j < E; ++j) g[j] = sc[j] * fmaf(g[j], db[j], dj[j]);
+    return lp + grp.sum(fldj);
+  }
+};
+
+// --------------------------------------------------------------------------
 // Logistic regression, data resident in shared memory: theta on lanes (E == 1,
 // D <= DT <= 32), rows strided over lanes.  X~ already carries the bias column.
 struct LogisticParams {
@@ -327,7 +396,11 @@ struct StochVolParams {
   int T;
 };
 
-template <class Grp, int E>
+// kFolded = true: state in UNCONSTRAINED coordinates [u_phi, m, u_s, z] with the default event-space bijector
+// (Sigmoid(-1, 1), Identity, Softplus, Identity; vectorized_stochastic_volatility.py:346-356) and its log-det-Jacobian
+// folded into the target -- what a TransformedTransitionKernel over the constrained model evaluates;
+// kFolded = false: the model itself, state [phi, m, s, z] (persistence in (-1, 1), shock scale > 0).
+template <class Grp, int E, bool kFolded = true>
 struct StochVolT {
   static_assert(Grp::kIsBlock && E >= 4, "stochastic volatility runs CTA-per-chain");
   using Params = StochVolParams;
@@ -360,8 +433,8 @@ struct StochVolT {
       const float u1 = x[0], mm = x[1], u3 = x[2];
       sg = sigmoidf(u1); sgm = sigmoidf(-u1);
       sg3 = sigmoidf(u3); sgm3 = sigmoidf(-u3);
-      const float phi0 = 2.f * sg - 1.f;
-      const float s0 = softplusf(u3);
+      const float phi0 = kFolded ? 2.f * sg - 1.f : u1;
+      const float s0 = kFolded ? softplusf(u3) : u3;
       const float rs0 = 1.0f / sqrtf(1.f - phi0 * phi0);
       const float b = (phi0 + 1.f) * 0.5f;
       // Beta(20,1.5).log_prob(b) - log 2 ; lbeta(20,1.5) = lgamma(20)+lgamma(1.5)-lgamma(21.5)
@@ -370,7 +443,7 @@ struct StochVolT {
       const float lp_m = -2.75416779828f - log1pf(m5 * m5);           // -log(pi*5)
       const float s2 = s0 * 0.5f;
       const float lp_s = 0.693147180559945f - 1.83787706640935f - log1pf(s2 * s2);  // log2 - log(2 pi)
-      const float fldj = (0.693147180559945f - softplusf(-u1) - softplusf(u1)) + (-softplusf(-u3));
+      const float fldj = kFolded ? (0.693147180559945f - softplusf(-u1) - softplusf(u1)) + (-softplusf(-u3)) : 0.f;
       prm[0] = phi0; prm[1] = mm; prm[2] = s0; prm[3] = rs0;
       prm[4] = lp_phi + lp_m + lp_s + fldj;
     }
@@ -471,9 +544,9 @@ struct StochVolT {
       const float d_m = sums[0] - (2.f * m / 25.f) / (1.f + m5 * m5);
       const float d_s = sums[3] - s2 / (1.f + s2 * s2);
       const float d_phi = sums[4] + lam0 * s * z0 * phi * rs * rs * rs + 0.5f * (19.f / b - 0.5f / (1.f - b));
-      g[0] = d_phi * (2.f * sg * sgm) + (sgm - sg);
+      g[0] = kFolded ? d_phi * (2.f * sg * sgm) + (sgm - sg) : d_phi;
       g[1] = d_m;
-      g[2] = d_s * sg3 + sgm3;
+      g[2] = kFolded ? d_s * sg3 + sgm3 : d_s;
     }
     return sums[1] + sums[2] + lp_params;
   }

@@ -158,6 +158,7 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
   if (tgt->dim <= 32 || tgt->dim > 100) return false;
   if (mode != kModeHMC && mode != kModeNUTS) return false;
   if (p.step_kind == 1) return false;                              // per-dimension step sizes: warp kernels
+  if (p.bij_kind) return false;                                    // event-space bijectors: warp kernels
   // the choice depends on the chains of the WHOLE job, so that every shard of a chain-sharded run takes the same path
   return std::max(p.B, p.B_global) >= 2 * kM;
 }

@@ -154,6 +154,9 @@ def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_bur
                     num_steps_between_results=int(num_steps_between_results), step_kind=int(step_kind),
                     explicit_step_seeds=0 if step_seeds is None else 1,
                     d_momentum_scale=None if momentum_scale is None else momentum_scale.data_ptr())
+  bij = target.bijector_arrays(x.device) if hasattr(target, 'bijector_arrays') else None
+  if bij is not None:   # TransformedTransitionKernel: x is the unconstrained state
+    cfg.d_bijector_kind, cfg.d_bijector_low, cfg.d_bijector_high = (b.data_ptr() for b in bij)
   n_steps = int(num_burnin_steps) + 1 + (int(num_results) - 1) * (1 + int(num_steps_between_results))
   if step_seeds is None:
     h_seed = np.ascontiguousarray(np.asarray(seed, np.uint32).reshape(2)).copy()

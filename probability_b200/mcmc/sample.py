@@ -113,8 +113,34 @@ def _fused_kernel(kernel):
 _NUTS_ROOT = tuple((f,) for f in nuts_lib.NoUTurnSampler._ALL)
 
 
+def _try_fused_transformed(kernel, num_results, current_state, pkr, num_burnin_steps, num_steps_between_results,
+                           trace_fn, seed, leapfrog_total):
+  """TransformedTransitionKernel around a fusable stack: the whole run happens in the unconstrained space (one pb2_run),
+  the traced states are mapped forward afterwards and `trace_fn` sees results nested under `inner_results`."""
+  from probability_b200.mcmc import transformed_kernel as ttk_lib
+  inner_trace = None if trace_fn is None else (
+      lambda s, kr: trace_fn(s, ttk_lib.TransformedTransitionKernelResults(transformed_state=None, inner_results=kr)))
+  if trace_fn is not None:
+    probe = _probe_trace_fn(trace_fn, current_state)
+    if probe is None or any((not q) or q[0] != 'inner_results' for q in probe[1]):
+      return None
+  out = _try_fused(kernel.inner_kernel, num_results, pkr.transformed_state, pkr.inner_results, num_burnin_steps,
+                   num_steps_between_results, inner_trace, seed, leapfrog_total)
+  if out is None:
+    return None
+  t_states, trace, final_inner, seed_out = out
+  was_list = _engine.is_list_like(t_states)
+  last = [s[-1] for s in t_states] if was_list else t_states[-1]
+  final = ttk_lib.TransformedTransitionKernelResults(transformed_state=last, inner_results=final_inner)
+  return kernel._forward(t_states), trace, final, seed_out
+
+
 def _try_fused(kernel, num_results, current_state, pkr, num_burnin_steps, num_steps_between_results,
                trace_fn, seed, leapfrog_total=None):
+  from probability_b200.mcmc import transformed_kernel as ttk_lib
+  if isinstance(kernel, ttk_lib.TransformedTransitionKernel):
+    return _try_fused_transformed(kernel, num_results, current_state, pkr, num_burnin_steps,
+                                  num_steps_between_results, trace_fn, seed, leapfrog_total)
   fk = _fused_kernel(kernel)
   if fk is None:
     return None

@@ -153,6 +153,25 @@ class StochasticVolatility(Target):
     return out
 
 
+class StochasticVolatilityConstrained(Target):
+  """The same model in its own (constrained) coordinates [persistence_of_volatility in (-1, 1), mean_log_volatility,
+  white_noise_shock_scale > 0, std_log_volatility[T]] -- what inference_gym's VectorizedStochasticVolatility.log_prob
+  takes (vectorized_stochastic_volatility.py:233-309).  Sample it through
+  `TransformedTransitionKernel(kernel, StochasticVolatilityConstrained.default_event_space_bijector())`."""
+  kind = _lib.TARGET_STOCH_VOL_CONSTRAINED
+
+  def __init__(self, centered_returns):
+    y = np.asarray(centered_returns, np.float32)
+    self.centered_returns = y
+    super().__init__(dim=y.size + 3, n_rows=y.size, a=y, part_sizes=[1, 1, 1, y.size])
+
+  @staticmethod
+  def default_event_space_bijector():
+    """vectorized_stochastic_volatility.py:346-356."""
+    from probability_b200 import bijectors as b
+    return [b.Sigmoid(-1., 1.), b.Identity(), b.Softplus(), b.Identity()]
+
+
 class RowShardedLogisticRegression(Target):
   """Large-data logistic regression whose ROWS are sharded over the ranks of a
   torch.distributed process group (BASELINE config 5).  Every rank holds all chains
