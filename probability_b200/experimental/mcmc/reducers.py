@@ -1,0 +1,166 @@
+"""Streaming reducers and `sample_fold` (tfp/experimental/mcmc/{reducer.py, expectations_reducer.py,
+covariance_reducer.py:38-220, potential_scale_reduction_reducer.py:36-160, sample_fold.py:35-180, with_reductions.py:41}):
+statistics of a chain without materialising its `[num_steps, chains, ...]` history.
+
+The reference folds one state per step into every reducer.  Here `sample_fold` advances the chain in bounded CHUNKS of
+fused transitions (one pb2_run per chunk) and every chunk of states `[n, chains, D]` is folded into running per-chain
+moments by ONE device pass (pb2_running_moments_update over the `[n, chains * D]` view: Welford / Chan, fixed order), so
+the memory in flight is the chunk, not the run.  Every reducer below is a function of those running moments.
+"""
+import collections
+
+import numpy as np
+
+from probability_b200 import _lib
+from probability_b200 import random as pb_random
+from probability_b200.mcmc import _engine
+from probability_b200.mcmc import sample as sample_lib
+
+
+class _ChainMoments(object):
+  """count, mean[B, D], sum of squared deviations[B, D] over the steps seen so far (per chain and dimension)."""
+
+  def __init__(self, B, D, device):
+    import torch
+    self.B, self.D = B, D
+    self.state = torch.zeros(1 + 2 * B * D, dtype=torch.float32, device=device)
+
+  def update(self, states):
+    """states: [n, B, D] float32 CUDA."""
+    x = states.reshape(states.shape[0], self.B * self.D).contiguous()
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.pb2_running_moments_update(ctx.handle, _lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(self.state)),
+               ctx.handle)
+
+  @property
+  def count(self):
+    return self.state[0]
+
+  @property
+  def mean(self):
+    return self.state[1:1 + self.B * self.D].reshape(self.B, self.D)
+
+  @property
+  def m2(self):
+    return self.state[1 + self.B * self.D:].reshape(self.B, self.D)
+
+
+class Reducer(object):
+  """reducer.py:27-110: `initialize(initial_chain_state, initial_kernel_results)`, `one_step(new_chain_state,
+  current_reducer_state, previous_kernel_results)`, `finalize(final_reducer_state)`.  `sample_fold` feeds these reducers
+  the shared running moments; `one_step` is provided for the per-step protocol (a chunk of one state)."""
+
+  def initialize(self, initial_chain_state, initial_kernel_results=None):
+    x, shapes, was_list = _engine.flatten_state(initial_chain_state)
+    st = _ChainMoments(x.shape[0], x.shape[1], x.device)
+    st.shapes, st.was_list = shapes, was_list
+    return st
+
+  def one_step(self, new_chain_state, current_reducer_state, previous_kernel_results=None):
+    x, _, _ = _engine.flatten_state(new_chain_state)
+    current_reducer_state.update(x[None])
+    return current_reducer_state
+
+  def finalize(self, final_reducer_state):
+    raise NotImplementedError
+
+  @staticmethod
+  def _unflat(st, v):
+    return _engine.unflatten(v, st.shapes, st.was_list)
+
+
+class ExpectationsReducer(Reducer):
+  """expectations_reducer.py:30-130 with the identity transform: running mean of the state, per chain."""
+
+  def finalize(self, st):
+    return self._unflat(st, st.mean)
+
+
+class VarianceReducer(Reducer):
+  """covariance_reducer.py:223-290: running variance of the state over the steps, per chain (`ddof` as there)."""
+
+  def __init__(self, ddof=0):
+    self.ddof = ddof
+
+  def finalize(self, st):
+    return self._unflat(st, st.m2 / (st.count - float(self.ddof)))
+
+
+class PotentialScaleReductionReducer(Reducer):
+  """potential_scale_reduction_reducer.py:36-160: R-hat from per-chain running means and variances
+  (diagnostic.py:476-567 with independent_chain_ndims = 1)."""
+
+  def __init__(self, independent_chain_ndims=1):
+    if independent_chain_ndims != 1:
+      raise NotImplementedError('one chain axis')
+
+  def finalize(self, st):
+    n, m = st.count, float(st.B)
+    if st.B < 2:
+      raise ValueError('Must provide at least 2 chains.')
+    chain_var = st.m2 / (n - 1.0)                       # within-chain variances (ddof = 1)
+    w = chain_var.mean(0)
+    b_div_n = st.mean.var(0, unbiased=True)             # variance of the chain means
+    rhat = ((m + 1.0) / m) * (((n - 1.0) / n) * w + b_div_n) / w - (n - 1.0) / (m * n)
+    return _unflat_event(st, rhat)
+
+
+def _unflat_event(st, v):
+  """[D] -> the state's structure without the chain axis."""
+  sizes = _engine.part_sizes_of(st.shapes)
+  outs, off = [], 0
+  for s, n in zip(st.shapes, sizes):
+    outs.append(v[off:off + n].reshape(s))
+    off += n
+  return outs if st.was_list else outs[0]
+
+
+SampleFoldResults = collections.namedtuple('SampleFoldResults', ['reduction_results', 'end_state',
+                                                                 'final_kernel_results'])
+
+
+def sample_fold(num_steps, current_state, previous_kernel_results=None, kernel=None, reducer=None,
+                previous_reducer_state=None, return_final_reducer_states=False, num_burnin_steps=0,
+                num_steps_between_results=0, parallel_iterations=10, seed=None, name=None,
+                experimental_chunk_bytes=256 << 20):
+  """sample_fold.py:35-180: `num_steps` results folded into `reducer` (a Reducer or a list of them); returns
+  `(reduction_results, end_state, final_kernel_results)`.  The chain advances in chunks of at most
+  `experimental_chunk_bytes` of states; chunk seeds are derived by `seed_chunk, seed = split_seed(seed)`."""
+  del parallel_iterations, name
+  import torch
+  if kernel is None:
+    raise ValueError('`kernel` is required')
+  reducers = list(reducer) if isinstance(reducer, (list, tuple)) else [reducer]
+  single = not isinstance(reducer, (list, tuple))
+  seed = pb_random.sanitize_seed(seed, salt='mcmc.sample_fold')
+  if previous_kernel_results is None:
+    previous_kernel_results = kernel.bootstrap_results(current_state)
+  x, shapes, was_list = _engine.flatten_state(current_state)
+  B, D = x.shape
+  shared = previous_reducer_state
+  if shared is None:
+    shared = _ChainMoments(B, D, x.device)
+    shared.shapes, shared.was_list = shapes, was_list
+  chunk = int(max(1, min(int(num_steps), experimental_chunk_bytes // max(1, 4 * B * D))))
+  state, pkr = current_state, previous_kernel_results
+  done = 0
+  while done < int(num_steps):
+    n = min(chunk, int(num_steps) - done)
+    cseed, seed = pb_random.split_seed(seed)
+    res = sample_lib.sample_chain(n, state, previous_kernel_results=pkr, kernel=kernel, trace_fn=None,
+                                  num_burnin_steps=num_burnin_steps if done == 0 else num_steps_between_results,
+                                  num_steps_between_results=num_steps_between_results,
+                                  return_final_kernel_results=True, seed=cseed)
+    st = res.all_states
+    flat = torch.cat([s.reshape(s.shape[0], s.shape[1], -1) for s in st], -1) if was_list else st.reshape(n, B, D)
+    shared.update(flat)
+    state = [s[-1] for s in st] if was_list else st[-1]
+    pkr = res.final_kernel_results
+    done += n
+    del res, st, flat
+  results = [r.finalize(shared) if r is not None else None for r in reducers]
+  out = results[0] if single else results
+  if return_final_reducer_states:
+    out = (out, shared)
+  return SampleFoldResults(out, state, pkr)

@@ -246,3 +246,35 @@ def test_windowed_adaptive_nuts_ill_conditioned_gaussian(tfp):
   # posterior variances within 4 MCSE-ish of the truth
   var_hat = draws.reshape(-1, 100).var(0).cpu().numpy()
   np.testing.assert_allclose(var_hat, truth, rtol=0.15)
+
+
+def test_sample_fold_streaming_reducers(tfp):
+  """experimental/mcmc/sample_fold.py + reducers: mean / variance / R-hat of a run computed from running moments, chunk
+  by chunk, equal the statistics of the materialised history of the same chunked run."""
+  tg, og, x, _ = _targets(tfp, 'eight_schools')
+  exp = tfp.experimental.mcmc
+  state = _parts(tg, x)
+  k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.3, num_leapfrog_steps=3)
+  n_steps = 57
+  red = [exp.ExpectationsReducer(), exp.VarianceReducer(), exp.PotentialScaleReductionReducer()]
+  chunk_bytes = 10 * x.shape[0] * x.shape[1] * 4       # chunks of 10 steps: 6 chunks, the last one short
+  out = exp.sample_fold(n_steps, state, kernel=k, reducer=red, seed=21, experimental_chunk_bytes=chunk_bytes)
+  mean, var, rhat = out.reduction_results
+  # the same chunked run, materialised
+  seed = tfp.random.sanitize_seed(21, salt='mcmc.sample_fold')
+  st, pkr, hist, done = state, k.bootstrap_results(state), [], 0
+  while done < n_steps:
+    n = min(10, n_steps - done)
+    cs, seed = tfp.random.split_seed(seed)
+    r = tfp.mcmc.sample_chain(n, st, previous_kernel_results=pkr, kernel=k, trace_fn=None, seed=cs,
+                              return_final_kernel_results=True)
+    hist.append(_flat([s.reshape(-1, *s.shape[2:]) for s in r.all_states]).reshape(n, x.shape[0], -1))
+    st, pkr, done = [s[-1] for s in r.all_states], r.final_kernel_results, done + n
+  h = np.concatenate(hist).astype(np.float64)            # [n_steps, B, D]
+  np.testing.assert_allclose(_flat(mean), h.mean(0), rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(_flat(var), h.var(0), rtol=2e-3, atol=1e-5)
+  ref_rhat = tfp.mcmc.potential_scale_reduction(t(h.astype(np.float32)), split_chains=False).cpu().numpy()
+  got_rhat = np.concatenate([np.atleast_1d(v.cpu().numpy()).reshape(-1) for v in rhat])
+  np.testing.assert_allclose(got_rhat, ref_rhat, rtol=2e-3)
+  for a, b in zip(out.end_state, st):
+    np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
