@@ -229,8 +229,9 @@ struct Chain {
     bool accepted, reach_max_depth, has_divergence;
   };
 
+  static constexpr int kColdVectors = 7;   // om, ox, og, cx, cgd, bx, bg
   __device__ void nuts_transition(int t, float (&x)[E], float& lp, float (&g)[E], float* ckm, float* ckr,
-                                  NutsOut& out) {
+                                  float* cold, NutsOut& out) {
     const uint32_t* sk = p.sched + (size_t)(t - p.t_sched0) * p.sched_stride;
     const uint32_t* hdr = sk + 2 * p.n_parts;                  // per depth: dir key, acc key, sub key
     const uint32_t* ku = hdr + 6 * p.max_depth;                // subtree uniform keys, depth j at 2^j - 1
@@ -244,10 +245,14 @@ struct Chain {
       rb[j] = (float)(chain_bits(hdr + 6 * j) & 1u);
       rb[16 + j] = log1pf(-uniform_from_bits(chain_bits(hdr + 6 * j + 2), 0.f, 1.f));
     }
+    using ColdV = typename Grp::template Cold<E>;
     float sm[E], sx[E], sg[E], slp;      // moving end
-    float om[E], ox[E], og[E], olp;      // other end
-    float cx[E], cgd[E], clp, cen, cw;   // candidate
-    float bx[E], bg[E], blp, ben, bw;    // subtree candidate
+    ColdV om(cold, 0, grp.lane), ox(cold, 1, grp.lane), og(cold, 2, grp.lane);   // other end
+    float olp;
+    ColdV cx(cold, 3, grp.lane), cgd(cold, 4, grp.lane);                         // candidate
+    float clp, cen, cw;
+    ColdV bx(cold, 5, grp.lane), bg(cold, 6, grp.lane);                          // subtree candidate
+    float blp, ben, bw;
     float rho[E], rhos[E];
     draw_momentum(sk, sm);               // nuts.py:515-523
     const float H0 = lp - 0.5f * sumsq(sm);  // compute_hamiltonian :1085-1102

@@ -14,10 +14,19 @@ struct SmemPlan {
   int tgt_off;       // offset of target group smem inside the group region
   int ck_off;        // offset of checkpoint store inside the group region (-1: global)
   int ck_floats;     // floats per checkpoint array (m or rho)
+  int cold_off;      // block groups, NUTS: offset of the cold vectors inside the group region (-1: registers)
 };
 
+// CTAs per SM of the CTA-per-chain (block group) kernels: a chain's leapfrog is a chain of block-wide scans and
+// reductions separated by barriers (latency-bound), so a second resident CTA -- another chain -- fills the gaps
+#ifndef PB2_BLOCK_GROUP_CTAS_PER_SM
+#define PB2_BLOCK_GROUP_CTAS_PER_SM 1
+#endif
+template <class Grp>
+constexpr int min_ctas_per_sm() { return Grp::kIsBlock ? PB2_BLOCK_GROUP_CTAS_PER_SM : 1; }
+
 template <class Grp, int E, class Tgt, int MODE, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
+__global__ void __launch_bounds__(MAXT, min_ctas_per_sm<Grp>())
 chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io, const SmemPlan plan) {
   extern __shared__ __align__(16) float smem[];
   float* cta = smem;
@@ -82,7 +91,7 @@ chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io
           nleap_total += (unsigned long long)p.L;
         } else {
           typename Chain<Grp, E, Tgt>::NutsOut no;
-          ch.nuts_transition(t, x, lp, g, ckm, ckr, no);
+          ch.nuts_transition(t, x, lp, g, ckm, ckr, plan.cold_off >= 0 ? gbase + plan.cold_off : nullptr, no);
           nleap_total += (unsigned long long)no.leapfrogs;
           if (p.lar_last && grp.lane == 0) p.lar_last[cc] = no.log_accept_ratio;
           if (r >= 0 && grp.lane == 0) {
@@ -134,6 +143,11 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
       gf += 2 * plan.ck_floats;
     }
   }
+  plan.cold_off = -1;
+  if (MODE == kModeNUTS && Grp::kColdInSmem) {
+    plan.cold_off = gf;
+    gf += Chain<Grp, E, Tgt>::kColdVectors * E * Grp::G;
+  }
   plan.group_floats = gf;
   const size_t cta_bytes = 4ull * (plan.cta_floats + plan.red_floats);
   const size_t grp_bytes = 4ull * gf;
@@ -141,7 +155,7 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
   if (Grp::kIsBlock) {
     threads = Grp::G;
     warps = 1;  // groups per CTA
-    grid = std::min(p.B, ctx->num_sms);
+    grid = std::min(p.B, ctx->num_sms * min_ctas_per_sm<Grp>());
   } else {
     if (cta_bytes + grp_bytes > (size_t)ctx->max_smem_optin)
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "target data does not fit in shared memory");

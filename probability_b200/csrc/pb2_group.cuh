@@ -19,6 +19,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 struct WarpG {
   static constexpr int G = 32;
   static constexpr bool kIsBlock = false;
+  // "cold" NUTS vectors (other end, candidates): registers for the small groups
+  static constexpr bool kColdInSmem = false;
+  template <int E>
+  struct Cold {
+    float v[E];
+    __device__ __forceinline__ Cold(float*, int, int) {}
+    __device__ __forceinline__ float& operator[](int j) { return v[j]; }
+    __device__ __forceinline__ const float& operator[](int j) const { return v[j]; }
+  };
   int lane;
   float* scratch;  // per-group shared scratch (>= 64 floats), see chain kernels
   __device__ WarpG(float* s) : lane(threadIdx.x & 31), scratch(s) {}
@@ -42,6 +51,15 @@ struct WarpG {
 struct HalfWarpG {
   static constexpr int G = 16;
   static constexpr bool kIsBlock = false;
+  // "cold" NUTS vectors (other end, candidates): registers for the small groups
+  static constexpr bool kColdInSmem = false;
+  template <int E>
+  struct Cold {
+    float v[E];
+    __device__ __forceinline__ Cold(float*, int, int) {}
+    __device__ __forceinline__ float& operator[](int j) { return v[j]; }
+    __device__ __forceinline__ const float& operator[](int j) const { return v[j]; }
+  };
   int lane;        // 0..15 inside the half
   unsigned mask;   // lanes of this half
   float* scratch;
@@ -70,6 +88,17 @@ struct BlockG {
   static constexpr int G = 32 * NW;
   static constexpr bool kIsBlock = true;
   static constexpr int kMaxN = 8;
+  // "cold" NUTS vectors (other end, trajectory / subtree candidates: touched at doubling boundaries and on a
+  // multinomial take, not in every leapfrog) live in shared memory, one private slot per thread and element
+  // ([vector][element][thread]: conflict-free), so that the hot state fits the register budget of two CTAs per SM
+  static constexpr bool kColdInSmem = true;
+  template <int E>
+  struct Cold {
+    float* p;
+    __device__ __forceinline__ Cold(float* base, int k, int lane) : p(base + (size_t)k * E * G + lane) {}
+    __device__ __forceinline__ float& operator[](int j) { return p[j * G]; }
+    __device__ __forceinline__ const float& operator[](int j) const { return p[j * G]; }
+  };
   int lane;
   float* scratch;
   float* red;  // [2][kMaxN][NW] double-buffered partials: one __syncthreads per reduction
@@ -79,21 +108,24 @@ struct BlockG {
   template <int N>
   __device__ __forceinline__ void sumN(float (&v)[N]) {
     static_assert(N <= kMaxN, "too many simultaneous reductions");
+    static_assert(NW <= 32 && (NW & (NW - 1)) == 0, "second stage is a butterfly over the warp partials");
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
     float* buf = red + parity * (kMaxN * NW);
     parity ^= 1;
-    const int w = lane >> 5;
-    if ((lane & 31) == 0) {
+    const int w = lane >> 5, wl = lane & 31;
+    if (wl == 0) {
 #pragma unroll
       for (int i = 0; i < N; ++i) buf[i * NW + w] = v[i];
     }
     __syncthreads();
+    // second stage: every warp loads the NW partials (one per lane) and folds them with the same butterfly, so all
+    // threads of the CTA end with identical bits (1 LDS + log2(NW) shuffles per value instead of NW loads and adds)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      float s = 0.f;
+      float s = buf[i * NW + (wl & (NW - 1))];
 #pragma unroll
-      for (int k = 0; k < NW; ++k) s += buf[i * NW + k];
+      for (int o = NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       v[i] = s;
     }
   }

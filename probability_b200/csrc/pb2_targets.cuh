@@ -472,8 +472,20 @@ struct StochVolT {
     float Aex = __shfl_up_sync(0xffffffffu, Ai, 1);
     if (wl == 0) { Bex = 0.f; Aex = 1.f; }
     __syncthreads();
-    float hw = 0.f;  // h entering this warp
-    for (int k = 0; k < w; ++k) hw = fmaf(wtf[2 * k], hw, wtf[2 * k + 1]);
+    // h entering this warp = the composition of the warp totals of warps 0 .. w - 1 applied to 0: an inclusive
+    // Kogge-Stone scan of the NW affine maps over the lanes (4 steps) instead of a serial loop of up to NW - 1 steps
+    float hw;
+    {
+      float At = wl < NW ? wtf[2 * wl] : 1.f, Bt = wl < NW ? wtf[2 * wl + 1] : 0.f;
+#pragma unroll
+      for (int o = 1; o < NW; o <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, At, o);
+        const float Bp = __shfl_up_sync(0xffffffffu, Bt, o);
+        if (wl >= o) { Bt = fmaf(At, Bp, Bt); At *= Ap; }
+      }
+      hw = __shfl_sync(0xffffffffu, Bt, w > 0 ? w - 1 : 0);
+      if (w == 0) hw = 0.f;
+    }
     const float hin = fmaf(Aex, hw, Bex);
     float h[E], a[E];
     float hcur = hin;
@@ -513,8 +525,19 @@ struct StochVolT {
     float Arex = __shfl_down_sync(0xffffffffu, Ari, 1);
     if (wl == 31) { Brex = 0.f; Arex = 1.f; }
     __syncthreads();
-    float lw = 0.f;  // lambda entering this warp from the right
-    for (int k = NW - 1; k > w; --k) lw = fmaf(wtr[2 * k], lw, wtr[2 * k + 1]);
+    // lambda entering this warp from the right = warps NW - 1 .. w + 1 composed: the same scan, mirrored
+    float lw;
+    {
+      float At = wl < NW ? wtr[2 * wl] : 1.f, Bt = wl < NW ? wtr[2 * wl + 1] : 0.f;
+#pragma unroll
+      for (int o = 1; o < NW; o <<= 1) {
+        const float Ap = __shfl_down_sync(0xffffffffu, At, o);
+        const float Bp = __shfl_down_sync(0xffffffffu, Bt, o);
+        if (wl + o < NW) { Bt = fmaf(At, Bp, Bt); At *= Ap; }
+      }
+      lw = __shfl_sync(0xffffffffu, Bt, w + 1 < NW ? w + 1 : 0);
+      if (w + 1 >= NW) lw = 0.f;
+    }
     float lam = fmaf(Arex, lw, Brex);
     float s_lc = 0.f, s_lh = 0.f;
     float lam0 = 0.f, z0 = 0.f;
