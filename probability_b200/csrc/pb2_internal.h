@@ -73,8 +73,6 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
 // pb2_tile_nuts.cu (64-chain tiles: lock-step and asynchronous-lane NUTS)
 int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p);
-// pb2_tile128_nuts.cu (128-chain tiles, two threads per chain: lock-step and asynchronous-lane NUTS)
-int launch_tile128_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p, bool lockstep);
 
 // pb2_logistic_tc.cu
 int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g);

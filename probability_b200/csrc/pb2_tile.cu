@@ -177,12 +177,7 @@ int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "tile_hmc_kernel");
   }
-  if (mode == kModeNUTS) {
-    // 128-chain tiles (pb2_tile128_nuts.cu): asynchronous lanes, or the lock-step kernel (dense_variant 3 / shallow trees);
-    // dense_variant 4 / 5 keep the 64-chain tile kernels of pb2_tile_nuts.cu for A/B runs
-    if (ctx->dense_variant == 4 || ctx->dense_variant == 5) return launch_tile_nuts(ctx, tgt, p);
-    return launch_tile128_nuts(ctx, tgt, p, ctx->dense_variant == 3 || p.max_depth <= 5);
-  }
+  if (mode == kModeNUTS) return launch_tile_nuts(ctx, tgt, p);
   return set_error(ctx, PB2_ERR_UNSUPPORTED, "tile path: unsupported mode");
 }
 

@@ -858,9 +858,9 @@ int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p) {
   // P hi/lo planes + the previous leaf's checkpoint (momentum, rho) + the gradient exchange buffer
   const size_t smem = 2 * (size_t)kPlaneBytes + (2 * kVS + kXbufFloats) * sizeof(float);
   const int ntiles = (p.B + kM - 1) / kM;
-  // every lane at its own position of its own tree (dense_variant 4); lock-step kernel: dense_variant 5, or
-  // max_tree_depth <= 5
-  if (ctx->dense_variant != 5 && p.max_depth > kS0) {
+  // every lane at its own position of its own tree (the lock-step kernel remains as the literal batched algorithm:
+  // dense_variant 3, or max_tree_depth <= 5)
+  if (ctx->dense_variant != 3 && p.max_depth > kS0) {
     const int agrid = std::min(ntiles, getenv("PB2_ASYNC_GRID") ? atoi(getenv("PB2_ASYNC_GRID")) : ctx->num_sms);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t scr_bytes = up((size_t)agrid * async_scratch_vectors(p.max_depth) * kVS * sizeof(float));

@@ -65,12 +65,63 @@ def all_reduce_sum(t):
   return t
 
 
-def fold_in_axis_index(seed, rank=None, process_group=None):
-  """distribute_lib.fold_in_axis_index (:193-207): a different key on every rank of the axis (independent chains per
-  shard, experimental/mcmc/sharded.py:63-74).  Chain sharding through `experimental_chain_shard` does NOT need this:
-  there the RNG counters are the global chain indices and the sharded run equals the unsharded one bit for bit."""
+# ---- named axes (distribute_lib.py:33-73 canonicalize_named_axis, get_axis_index / get_axis_size) ---------------
+_AXES = {}   # name -> (index, size) or a torch.distributed process group
+
+
+def canonicalize_named_axis(named_axes):
+  """distribute_lib.canonicalize_named_axis: None -> [], 'a' -> ['a'], iterables -> list."""
+  if named_axes is None:
+    return []
+  if isinstance(named_axes, str):
+    return [named_axes]
+  return list(named_axes)
+
+
+def register_axis(name, index=None, size=None, process_group=None):
+  """Bind a named axis to a position: either an explicit (index, size) -- e.g. several shards driven by one process --
+  or a torch.distributed process group (the member index is this process's rank in it)."""
+  if process_group is not None:
+    _AXES[name] = process_group
+  else:
+    if index is None or size is None or not 0 <= int(index) < int(size):
+      raise ValueError('register_axis needs 0 <= index < size or a process group')
+    _AXES[name] = (int(index), int(size))
+
+
+def unregister_axis(name):
+  _AXES.pop(name, None)
+
+
+def _axis(name):
+  import torch.distributed as dist
+  a = _AXES.get(name)
+  if isinstance(a, tuple):
+    return a
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(a), dist.get_world_size(a)
+  return 0, 1
+
+
+def get_axis_index(name):
+  return _axis(name)[0]
+
+
+def get_axis_size(name):
+  return _axis(name)[1]
+
+
+def fold_in_axis_index(seed, axis_name=None):
+  """distribute_lib.fold_in_axis_index (:193-207): fold the index of this process along every named axis into the key,
+  i.e. a different key on every member (independent chains per shard, experimental/mcmc/sharded.py:63-74).  An int is
+  taken as the axis index itself.  Chain sharding through `experimental_chain_shard` does NOT need this: there the RNG
+  counters are the global chain indices and the sharded run equals the unsharded one bit for bit."""
   from probability_b200 import random as pb_random
-  if rank is None:
-    import torch.distributed as dist
-    rank = dist.get_rank(process_group) if (dist.is_available() and dist.is_initialized()) else 0
-  return pb_random.fold_in(pb_random.sanitize_seed(seed), int(rank))
+  if axis_name is None:
+    return seed
+  k = pb_random.sanitize_seed(seed)
+  if isinstance(axis_name, int):
+    return pb_random.fold_in(k, int(axis_name))
+  for name in canonicalize_named_axis(axis_name):
+    k = pb_random.fold_in(k, get_axis_index(name))
+  return k

@@ -196,3 +196,25 @@ def run(target, x, lp, g, step, step_kind, shapes, *, kind, num_results, num_bur
     if name in out:
       out[name] = out[name].bool()
   return out, h_seed, h_steps
+
+
+def check_shard_axis_names(shard_axis_names):
+  """State parts sharded over a named axis need the dot products of the transition psum'd over that axis
+  (hmc.py:706-716, nuts.py:994-998).  This engine keeps every chain's whole state on one GPU -- it shards chains
+  (ChainShard, Sharded) and data rows (RowShardedLogistic) instead -- so only axes of size 1 are accepted."""
+  from probability_b200 import distribute
+  if not shard_axis_names:
+    return
+  def names(s):
+    if isinstance(s, str):
+      return [s]
+    out = []
+    for e in s:
+      if e is not None:
+        out.extend(names(e))
+    return out
+  for name in names(shard_axis_names):
+    if distribute.get_axis_size(name) > 1:
+      raise NotImplementedError(
+          'experimental_shard_axis_names: state parts sharded over axis {!r} (size {}) are not supported; shard the '
+          'chains (ChainShard / Sharded) or the data rows (RowShardedLogistic)'.format(name, distribute.get_axis_size(name)))

@@ -68,6 +68,7 @@ class UncalibratedHamiltonianMonteCarlo(kernel_base.TransitionKernel):
         store_parameters_in_results=store_parameters_in_results,
         experimental_shard_axis_names=experimental_shard_axis_names, name=name)
     self._target = _engine.require_target(target_log_prob_fn)
+    _engine.check_shard_axis_names(experimental_shard_axis_names)
 
   target_log_prob_fn = property(lambda self: self._parameters['target_log_prob_fn'])
   step_size = property(lambda self: self._parameters['step_size'])
@@ -205,6 +206,7 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
         experimental_shard_axis_names=experimental_shard_axis_names,
         experimental_chain_shard=experimental_chain_shard, name=name)
     self._target = _engine.require_target(target_log_prob_fn)
+    _engine.check_shard_axis_names(experimental_shard_axis_names)
     self._impl = MetropolisHastings(UncalibratedHamiltonianMonteCarlo(
         target_log_prob_fn, step_size, num_leapfrog_steps,
         store_parameters_in_results=store_parameters_in_results))

@@ -29,7 +29,12 @@ class TransitionKernel(metaclass=abc.ABCMeta):
 
   @property
   def experimental_shard_axis_names(self):
-    return []
+    """Named axes over which the state parts are sharded (kernel.py:117-126); none unless the kernel takes the
+    `experimental_shard_axis_names` parameter."""
+    return self.parameters.get('experimental_shard_axis_names') or []
 
   def experimental_with_shard_axes(self, shard_axis_names):
+    """A copy of the kernel whose state parts are sharded over `shard_axis_names` (hmc.py:686-687, nuts.py:516-517)."""
+    if 'experimental_shard_axis_names' in self.parameters:
+      return self.copy(experimental_shard_axis_names=shard_axis_names)
     return self

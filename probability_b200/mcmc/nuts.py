@@ -87,6 +87,7 @@ class NoUTurnSampler(kernel_base.TransitionKernel):
         parallel_iterations=parallel_iterations, experimental_shard_axis_names=experimental_shard_axis_names,
         experimental_chain_shard=experimental_chain_shard, name=name)
     self._target = _engine.require_target(target_log_prob_fn)
+    _engine.check_shard_axis_names(experimental_shard_axis_names)
     self._write_instruction, self._read_instruction = generate_efficient_write_read_instruction(
         max_tree_depth)
 

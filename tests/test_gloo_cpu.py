@@ -65,6 +65,15 @@ def _worker(rank, world, port, q):
     packed = torch.tensor(lik(X[lo:hi], y[lo:hi]))
     dist.all_reduce(packed)
     np.testing.assert_allclose(packed.numpy(), lik(X, y), rtol=1e-10)
+    # (iv) Sharded / fold_in_axis_index: an unregistered axis name is the world -- every rank folds its own rank into
+    # the key (distribute_lib.py:193-207), so the ranks' keys differ and match the oracle's fold_in
+    from probability_b200 import distribute
+    mine = distribute.fold_in_axis_index(orng.key(9), 'ranks')
+    np.testing.assert_array_equal(mine, orng.fold_in(orng.key(9), rank))
+    assert distribute.get_axis_size('ranks') == world
+    ks = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(ks, torch.tensor(mine.astype(np.int64)))
+    assert len({tuple(k.tolist()) for k in ks}) == world
     q.put((rank, 'ok'))
   except Exception as e:  # pylint: disable=broad-except
     q.put((rank, 'FAIL: %r' % (e,)))
