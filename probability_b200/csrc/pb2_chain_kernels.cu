@@ -20,7 +20,7 @@ struct SmemPlan {
 // CTAs per SM of the CTA-per-chain (block group) kernels: a chain's leapfrog is a chain of block-wide scans and
 // reductions separated by barriers (latency-bound), so a second resident CTA -- another chain -- fills the gaps
 #ifndef PB2_BLOCK_GROUP_CTAS_PER_SM
-#define PB2_BLOCK_GROUP_CTAS_PER_SM 1
+#define PB2_BLOCK_GROUP_CTAS_PER_SM 2
 #endif
 template <class Grp>
 constexpr int min_ctas_per_sm() { return Grp::kIsBlock ? PB2_BLOCK_GROUP_CTAS_PER_SM : 1; }
