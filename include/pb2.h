@@ -47,6 +47,10 @@ extern "C" {
 /* RNG counter layouts (jax_threefry_partitionable True / False). */
 #define PB2_LAYOUT_PARTITIONABLE 0
 #define PB2_LAYOUT_ORIGINAL 1
+/* Philox-4x32-10 bit generator (the generator of tf.random.stateless_* behind samplers.py:249-250,324-325 on the TF
+ * substrate): element j of a flat draw = word j % 4 of the block at counter j / 4 under the uint32[2] key;
+ * split(key, n) = bits(2n) reshaped; fold_in and the float transforms are those of the threefry layouts */
+#define PB2_LAYOUT_PHILOX 2
 
 /* target kinds */
 #define PB2_TARGET_EIGHT_SCHOOLS 0

@@ -15,6 +15,8 @@ al., SC'11) with jax's key/counter conventions.  Both counter layouts are kept:
       split child j is (out0, out1) of counter (0, j).
   ORIGINAL: counters iota(n) padded to even, first half -> x0, second half -> x1,
       output concat(out0, out1)[:n]; split = bits(2n).reshape(n, 2).
+A third generator, PHILOX, draws the same flat streams from Philox4x32-10 (key = the uint32[2] key, element j = word
+j % 4 of counter block j // 4; split = bits(2n).reshape(n, 2); fold_in and the float transforms are unchanged).
 """
 import hashlib
 
@@ -22,6 +24,7 @@ import numpy as np
 
 PARTITIONABLE = 0
 ORIGINAL = 1
+PHILOX = 2   # Philox4x32-10 bit generator (north_star: "Philox counter RNG keyed from samplers.split_seed")
 
 _ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
 _U32 = np.uint32
@@ -51,6 +54,25 @@ def threefry2x32(k0, k1, x0, x1):
     return x0, x1
 
 
+def philox4x32_10(k0, k1, c0, c1, c2, c3):
+  """Philox-4x32, 10 rounds (Salmon et al., SC'11; the generator behind tf.random.stateless_* on the TF substrate,
+  samplers.py:249-250,324-325,367-368).  Key = 2 words, counter = 4 words; returns the 4 output words."""
+  M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+  W0, W1 = _U32(0x9E3779B9), _U32(0xBB67AE85)
+  with np.errstate(over='ignore'):
+    k0 = np.asarray(k0, _U32).copy(); k1 = np.asarray(k1, _U32).copy()
+    c = [np.asarray(v, _U32).copy() for v in (c0, c1, c2, c3)]
+    for _ in range(10):
+      p0 = c[0].astype(np.uint64) * M0
+      p1 = c[2].astype(np.uint64) * M1
+      hi0, lo0 = (p0 >> np.uint64(32)).astype(_U32), (p0 & np.uint64(0xFFFFFFFF)).astype(_U32)
+      hi1, lo1 = (p1 >> np.uint64(32)).astype(_U32), (p1 & np.uint64(0xFFFFFFFF)).astype(_U32)
+      c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+      k0 = k0 + W0
+      k1 = k1 + W1
+    return c
+
+
 def key(seed_int):
   """jax.random.PRNGKey(int) -> uint32[2] = [hi, lo]."""
   seed_int = int(seed_int)
@@ -69,6 +91,13 @@ def bits(k, n, layout=PARTITIONABLE):
     lo = (j & np.uint64(0xFFFFFFFF)).astype(_U32)
     o0, o1 = threefry2x32(k[0], k[1], hi, lo)
     return o0 ^ o1
+  if layout == PHILOX:
+    # element j = word j % 4 of the block at counter (j // 4, 0): 128-bit counter, low words first
+    j = np.arange(n, dtype=np.uint64)
+    blk = j >> np.uint64(2)
+    out = philox4x32_10(k[0], k[1], (blk & np.uint64(0xFFFFFFFF)).astype(_U32), (blk >> np.uint64(32)).astype(_U32),
+                        np.zeros(n, _U32), np.zeros(n, _U32))
+    return np.choose((j & np.uint64(3)).astype(np.int64), out).astype(_U32)
   cnt = np.arange(n, dtype=_U32)
   if n % 2:
     cnt = np.concatenate([cnt, np.zeros([1], _U32)])
@@ -84,7 +113,7 @@ def split(k, n=2, layout=PARTITIONABLE):
     j = np.arange(n, dtype=_U32)
     o0, o1 = threefry2x32(k[0], k[1], np.zeros_like(j), j)
     return np.stack([o0, o1], axis=-1)
-  return bits(k, 2 * n, ORIGINAL).reshape(n, 2)
+  return bits(k, 2 * n, layout).reshape(n, 2)
 
 
 def fold_in(k, data):

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get('PB2_LIB_PATH') or os.path.join(_HERE, '_C', 'libpb2.s
 PB2_OK = 0
 LAYOUT_PARTITIONABLE = 0
 LAYOUT_ORIGINAL = 1
+LAYOUT_PHILOX = 2
 TARGET_EIGHT_SCHOOLS, TARGET_DENSE_GAUSSIAN, TARGET_LOGISTIC, TARGET_STOCH_VOL = 0, 1, 2, 3
 TARGET_STOCH_VOL_CONSTRAINED = 4
 KERNEL_HMC, KERNEL_NUTS = 0, 1

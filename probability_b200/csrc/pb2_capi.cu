@@ -190,6 +190,8 @@ int pb2_target_dim(const pb2_target* t) { return t ? t->dim : PB2_ERR_INVALID; }
 // ------------------------------------------------------------------ RNG
 int pb2_rng_split(const uint32_t key[2], int n, int layout, uint32_t* h_out) {
   if (!key || !h_out || n < 0) return set_error(nullptr, PB2_ERR_INVALID, "pb2_rng_split: bad argument");
+  if (layout < PB2_LAYOUT_PARTITIONABLE || layout > PB2_LAYOUT_PHILOX)
+    return set_error(nullptr, PB2_ERR_INVALID, "pb2_rng_split: unknown generator layout");
   host_split(key, n, layout, h_out);
   return PB2_OK;
 }
@@ -205,6 +207,8 @@ int pb2_rng_fold_in(const uint32_t key[2], uint32_t data, uint32_t out[2]) {
 static int rng_fill(pb2_ctx* ctx, const uint32_t key[2], long long n, int layout, int what, float lo, float hi,
                     int ilo, int ihi, void* out) {
   if (!ctx || !key || (!out && n > 0) || n < 0) return set_error(ctx, PB2_ERR_INVALID, "pb2_rng_*: bad argument");
+  if (layout < PB2_LAYOUT_PARTITIONABLE || layout > PB2_LAYOUT_PHILOX)
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_rng_*: unknown generator layout");
   if (layout == PB2_LAYOUT_ORIGINAL && n >= (1ll << 32))
     return set_error(ctx, PB2_ERR_UNSUPPORTED, "original threefry layout: n must be < 2^32");
   Key k{key[0], key[1]}, kh{0, 0};
@@ -298,6 +302,8 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
     return set_error(ctx, PB2_ERR_INVALID, "pb2_run: NULL argument");
   if (lay->B < 0 || lay->B_global < lay->B || lay->chain_offset < 0 || lay->chain_offset + lay->B > lay->B_global)
     return set_error(ctx, PB2_ERR_INVALID, "pb2_run: inconsistent chain layout");
+  if (lay->rng_layout < PB2_LAYOUT_PARTITIONABLE || lay->rng_layout > PB2_LAYOUT_PHILOX)
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_run: unknown generator layout");
   if (lay->n_parts < 1 || lay->n_parts > kMaxParts) return set_error(ctx, PB2_ERR_INVALID, "pb2_run: need 1 <= n_parts <= 8");
   int sum = 0;
   for (int q = 0; q < lay->n_parts; ++q) {

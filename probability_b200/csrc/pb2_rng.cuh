@@ -1,4 +1,4 @@
-// Threefry-2x32-20 counter RNG with jax.random key/counter conventions.
+// Threefry-2x32-20 counter RNG with jax.random key/counter conventions (+ Philox-4x32-10 as a second bit generator).
 //
 // Replaces, on the device, what tfp/internal/samplers.py:200-368 calls on the JAX
 // substrate (jax.random.split / fold_in / uniform / normal / randint via
@@ -12,7 +12,7 @@
 
 namespace pb2 {
 
-enum : int { kLayoutPartitionable = 0, kLayoutOriginal = 1 };
+enum : int { kLayoutPartitionable = 0, kLayoutOriginal = 1, kLayoutPhilox = 2 };
 
 struct Key {
   uint32_t k0, k1;
@@ -44,9 +44,31 @@ PB2_HD void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uin
   o1 = x1;
 }
 
+// Philox-4x32-10 (Salmon et al., SC'11): the generator of tf.random.stateless_* on the reference's TF substrate
+// (samplers.py:249-250,324-325,367-368).  Word `w` of the block at 128-bit counter (c0, c1, 0, 0).
+PB2_HD uint32_t philox4x32_10_word(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, int w) {
+  uint32_t c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)c0 * 0xD2511F53ull, p1 = (uint64_t)c2 * 0xCD9E8D57ull;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return w == 0 ? c0 : (w == 1 ? c1 : (w == 2 ? c2 : c3));
+}
+
 // Element `idx` of a flat draw of `n` uint32 (row-major over the requested shape).
 PB2_HD uint32_t bits_at(Key k, uint64_t idx, uint64_t n, int layout) {
   uint32_t o0, o1;
+  if (layout == kLayoutPhilox) {
+    const uint64_t blk = idx >> 2;
+    return philox4x32_10_word(k.k0, k.k1, (uint32_t)blk, (uint32_t)(blk >> 32), (int)(idx & 3));
+  }
   if (layout == kLayoutPartitionable) {
     threefry2x32(k.k0, k.k1, (uint32_t)(idx >> 32), (uint32_t)idx, o0, o1);
     return o0 ^ o1;

@@ -15,6 +15,7 @@ from probability_b200 import _lib
 
 PARTITIONABLE = _lib.LAYOUT_PARTITIONABLE
 ORIGINAL = _lib.LAYOUT_ORIGINAL
+PHILOX = _lib.LAYOUT_PHILOX
 
 # jax_threefry_partitionable: True is the default of current JAX releases.
 _default_layout = PARTITIONABLE
@@ -23,6 +24,17 @@ _default_layout = PARTITIONABLE
 def set_threefry_partitionable(flag):
   global _default_layout
   _default_layout = PARTITIONABLE if flag else ORIGINAL
+
+
+def set_generator(name):
+  """Bit generator of every draw and key split: 'threefry' (jax.random's threefry2x32, partitionable layout -- the
+  default, bit-exact with the JAX substrate), 'threefry_original' (jax_threefry_partitionable=False) or 'philox'
+  (Philox4x32-10, the generator behind tf.random.stateless_* on the reference's TF substrate)."""
+  global _default_layout
+  layouts = {'threefry': PARTITIONABLE, 'threefry_original': ORIGINAL, 'philox': PHILOX}
+  if name not in layouts:
+    raise ValueError('generator must be one of {}, got {!r}'.format(sorted(layouts), name))
+  _default_layout = layouts[name]
 
 
 def default_layout():

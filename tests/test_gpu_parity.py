@@ -37,7 +37,7 @@ def rel_err(a, b):
 
 
 # ------------------------------------------------------------------ RNG
-@pytest.mark.parametrize('layout', [0, 1])
+@pytest.mark.parametrize('layout', [0, 1, 2])   # threefry partitionable / original, Philox4x32-10
 @pytest.mark.parametrize('n', [1, 2, 7, 64, 1001, 65536])
 def test_rng_streams_bit_exact(tfp, layout, n):
   for seed in (0, 17, 2**40 + 5):
@@ -205,11 +205,11 @@ def _flat(state):
   return state.cpu().numpy()
 
 
-@pytest.mark.parametrize('layout', [0, 1])
+@pytest.mark.parametrize('layout', [0, 1, 2])   # threefry partitionable / original, Philox4x32-10
 @pytest.mark.parametrize('which,eps,L', [('eight_schools', 0.4, 3), ('dense3', 0.6, 4), ('logistic5', 0.2, 3),
                                         ('sv60', 0.02, 3)])
 def test_hmc_one_step_matches_oracle(tfp, which, eps, L, layout):
-  tfp.random.set_threefry_partitionable(layout == 0)
+  tfp.random.set_generator(('threefry', 'threefry_original', 'philox')[layout])
   try:
     tg, o32, _, x = _targets(tfp, which)
     state = _parts(tg, x)
@@ -270,11 +270,11 @@ def test_hmc_nan_and_inf_reject(tfp):
 
 
 # ------------------------------------------------------------------ NUTS
-@pytest.mark.parametrize('layout', [0, 1])
+@pytest.mark.parametrize('layout', [0, 1, 2])   # threefry partitionable / original, Philox4x32-10
 @pytest.mark.parametrize('which,eps,depth', [('eight_schools', 0.3, 6), ('dense3', 0.5, 5), ('dense100', 0.3, 4),
                                             ('logistic5', 0.15, 5), ('logistic25', 0.03, 4), ('sv60', 0.03, 4)])
 def test_nuts_one_step_matches_oracle(tfp, which, eps, depth, layout):
-  tfp.random.set_threefry_partitionable(layout == 0)
+  tfp.random.set_generator(('threefry', 'threefry_original', 'philox')[layout])
   try:
     tg, o32, _, x = _targets(tfp, which)
     x = x[:64]
