@@ -58,6 +58,7 @@ extern "C" {
 #define PB2_TARGET_LOGISTIC 2
 #define PB2_TARGET_STOCH_VOL 3
 #define PB2_TARGET_STOCH_VOL_CONSTRAINED 4 /* the same model in its own coordinates [persistence, mean, scale, z] */
+#define PB2_TARGET_USER 5 /* user-defined: CUDA source compiled at run time, see pb2_target_create_user */
 
 /* elementwise event-space bijectors (one per state dimension), tfp/bijectors/{identity,exp,softplus,sigmoid}.py */
 #define PB2_BIJECTOR_IDENTITY 0
@@ -104,6 +105,21 @@ typedef struct {
 } pb2_target_desc;
 
 int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* desc, pb2_target** out);
+/* User-defined target = the reference's arbitrary `target_log_prob_fn` (tfp/mcmc/hmc.py:413-415,
+ * mcmc/internal/util.py:246-308 value + gradient; inference_gym model_contract.md `unnormalized_log_prob`).  A
+ * persistent kernel cannot call back into the host, so the target is CUDA C++ source defining, for ONE chain,
+ *     __device__ float target_log_prob_and_grad(const float* x, float* g, const float* data, int n_data);
+ * (returns log p(x) up to a constant, writes the gradient into g[0..dim)).  It is compiled with NVRTC for sm_100a
+ * together with csrc/pb2_user_target.cuh (`include_dir` = the directory holding the pb2 device headers) into the same
+ * leapfrog / HMC / NUTS chain kernels the named targets use; 1 <= dim <= 256; `h_data` (n_data floats, may be NULL) is
+ * copied to the device and handed to every call.  With PB2_USER_COOPERATIVE in `flags` the function takes a trailing
+ * `int lane` and is called by all 32 lanes of the chain's warp (x, g in shared memory; every lane writes a disjoint
+ * part of g and all return the same value).  On a compile error the call fails with PB2_ERR_INVALID and
+ * pb2_last_error returns the compiler's log.  pb2_user_target_check only compiles (no device needed). */
+#define PB2_USER_COOPERATIVE 1
+int pb2_target_create_user(pb2_ctx* ctx, int dim, const char* cuda_source, int flags, const float* h_data,
+                           long long n_data, const char* include_dir, pb2_target** out);
+int pb2_user_target_check(const char* cuda_source, int dim, int flags, const char* include_dir);
 int pb2_target_destroy(pb2_target* tgt);
 int pb2_target_dim(const pb2_target* tgt);
 

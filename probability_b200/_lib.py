@@ -19,6 +19,8 @@ LAYOUT_ORIGINAL = 1
 LAYOUT_PHILOX = 2
 TARGET_EIGHT_SCHOOLS, TARGET_DENSE_GAUSSIAN, TARGET_LOGISTIC, TARGET_STOCH_VOL = 0, 1, 2, 3
 TARGET_STOCH_VOL_CONSTRAINED = 4
+TARGET_USER = 5
+CSRC_DIR = os.path.join(_HERE, 'csrc')   # the device headers a user-defined target is compiled against (NVRTC)
 KERNEL_HMC, KERNEL_NUTS = 0, 1
 STEP_SCALAR, STEP_PER_DIM, STEP_PER_CHAIN = 0, 1, 2
 
@@ -92,6 +94,8 @@ def load():
         'pb2_launch_count': ([vp], ll),
         'pb2_ctx_set_int': ([vp, C.c_char_p, i32], i32),
         'pb2_target_create': ([vp, C.POINTER(TargetDesc), C.POINTER(vp)], i32),
+        'pb2_target_create_user': ([vp, i32, C.c_char_p, i32, c_f32p, ll, C.c_char_p, C.POINTER(vp)], i32),
+        'pb2_user_target_check': ([C.c_char_p, i32, i32, C.c_char_p], i32),
         'pb2_target_destroy': ([vp], i32),
         'pb2_target_dim': ([vp], i32),
         'pb2_rng_split': ([c_u32p, i32, i32, c_u32p], i32),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_C')
 LIB = os.path.join(OUT_DIR, 'libpb2.so')
-SOURCES = ['pb2_chain_kernels.cu', 'pb2_misc.cu', 'pb2_capi.cu', 'pb2_rowshard.cu', 'pb2_dense_tc.cu', 'pb2_tile.cu', 'pb2_tile_nuts.cu', 'pb2_logistic_tc.cu', 'pb2_comm.cu']
+SOURCES = ['pb2_chain_kernels.cu', 'pb2_misc.cu', 'pb2_capi.cu', 'pb2_rowshard.cu', 'pb2_dense_tc.cu', 'pb2_tile.cu', 'pb2_tile_nuts.cu', 'pb2_logistic_tc.cu', 'pb2_comm.cu', 'pb2_user.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

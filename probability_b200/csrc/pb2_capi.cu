@@ -176,8 +176,45 @@ int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* d, pb2_target** out) 
   return PB2_OK;
 }
 
+int pb2_user_target_check(const char* cuda_source, int dim, int flags, const char* include_dir) {
+  // all three builds: as written, diagonally preconditioned, behind bijectors
+  for (int variant = 0; variant < kUserVariants; ++variant) {
+    std::vector<char> cubin;
+    if (int rc = user_compile(nullptr, cuda_source, dim, include_dir, variant, flags, cubin)) return rc;
+  }
+  return PB2_OK;
+}
+
+int pb2_target_create_user(pb2_ctx* ctx, int dim, const char* cuda_source, int flags, const float* h_data,
+                           long long n_data, const char* include_dir, pb2_target** out) {
+  if (!ctx || !out || n_data < 0 || n_data > 0x7fffffffll || (n_data > 0 && !h_data))
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_target_create_user: bad argument");
+  cudaSetDevice(ctx->device);
+  if (!cuda_source || !include_dir) return set_error(ctx, PB2_ERR_INVALID, "pb2_target_create_user: NULL source");
+  pb2_target* t = new pb2_target();
+  t->ctx = ctx;
+  t->kind = PB2_TARGET_USER;
+  t->dim = dim;
+  t->n_rows = (int)n_data;
+  t->user_source = cuda_source;
+  t->user_include = include_dir;
+  t->user_flags = flags;
+  int rc = user_target_ensure(ctx, t, 0);   // the preconditioned / transformed variants are built on first use
+  if (!rc && n_data) {
+    rc = check_cuda(ctx, cudaMalloc(&t->d_a, (size_t)n_data * sizeof(float)), "cudaMalloc(user data)");
+    if (!rc) rc = check_cuda(ctx, cudaMemcpy(t->d_a, h_data, (size_t)n_data * sizeof(float), cudaMemcpyHostToDevice), "memcpy(user data)");
+  }
+  if (rc) {
+    pb2_target_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return PB2_OK;
+}
+
 int pb2_target_destroy(pb2_target* t) {
   if (!t) return PB2_OK;
+  user_target_unload(t);
   cudaFree(t->d_a);
   cudaFree(t->d_b);
   cudaFree(t->d_tc);

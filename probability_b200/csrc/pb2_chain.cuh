@@ -8,7 +8,7 @@
 // Per-chain early exit is result-identical to the reference's lock-step masking
 // because every key is a function of the step seed only.
 #pragma once
-#include <cstdint>
+#include "pb2_compat.cuh"
 #include "pb2_group.cuh"
 #include "pb2_rng.cuh"
 

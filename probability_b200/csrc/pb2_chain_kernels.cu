@@ -7,16 +7,6 @@
 
 namespace pb2 {
 
-struct SmemPlan {
-  int cta_floats;    // CTA-shared target data
-  int red_floats;    // block-group reduction buffers
-  int group_floats;  // per-group region (scratch + target + checkpoints)
-  int tgt_off;       // offset of target group smem inside the group region
-  int ck_off;        // offset of checkpoint store inside the group region (-1: global)
-  int ck_floats;     // floats per checkpoint array (m or rho)
-  int cold_off;      // block groups, NUTS: offset of the cold vectors inside the group region (-1: registers)
-};
-
 // CTAs per SM of the CTA-per-chain (block group) kernels: a chain's leapfrog is a chain of block-wide scans and
 // reductions separated by barriers (latency-bound), so a second resident CTA -- another chain -- fills the gaps
 #ifndef PB2_BLOCK_GROUP_CTAS_PER_SM
@@ -28,106 +18,31 @@ constexpr int min_ctas_per_sm() { return Grp::kIsBlock ? PB2_BLOCK_GROUP_CTAS_PE
 template <class Grp, int E, class Tgt, int MODE, int MAXT>
 __global__ void __launch_bounds__(MAXT, min_ctas_per_sm<Grp>())
 chain_kernel(const ChainParams p, const typename Tgt::Params tp, const PrimIO io, const SmemPlan plan) {
-  extern __shared__ __align__(16) float smem[];
-  float* cta = smem;
-  Tgt tgt;
-  tgt.init_cta(tp, cta);
-  __syncthreads();
-  float* gbase;
-  if constexpr (Grp::kIsBlock) gbase = smem + plan.cta_floats + plan.red_floats;
-  else gbase = smem + plan.cta_floats + (threadIdx.x / Grp::G) * plan.group_floats;
-  auto make_group = [&]() {
-    if constexpr (Grp::kIsBlock) return Grp(gbase, smem + plan.cta_floats);
-    else return Grp(gbase);
-  };
-  Grp grp = make_group();
-  tgt.init_group(tp, grp, cta, gbase + plan.tgt_off);
-  Chain<Grp, E, Tgt> ch(grp, tgt, p);
-  float* ckm = nullptr;
-  float* ckr = nullptr;
-  if constexpr (MODE == kModeNUTS) {
-    if (plan.ck_off >= 0) {
-      ckm = gbase + plan.ck_off;
-    } else {
-      ckm = p.ckpt_global + (size_t)blockIdx.x * 2 * plan.ck_floats;
-    }
-    ckr = ckm + plan.ck_floats;
-  }
-  while (true) {
-    int cc = 0;
-    if (grp.lane == 0) cc = atomicAdd(p.queue, 1);
-    cc = grp.bcast_int(cc, 0);
-    if (cc >= p.B) break;
-    ch.c = cc;
-    ch.cg = (uint64_t)p.chain_offset + (uint64_t)cc;
-    float x[E], g[E], lp;
-    if constexpr (MODE == kModeLogpGrad) {
-      ch.load_vec(io.x_in, x);
-      lp = tgt.logp_grad(grp, x, g);
-      ch.store_vec(io.g_out, 0, g);
-      if (grp.lane == 0) io.lp_out[cc] = lp;
-    } else if constexpr (MODE == kModeLeapfrog) {
-      float m[E], eps[E];
-      ch.load_vec(io.m_in, m);
-      ch.load_vec(io.x_in, x);
-      ch.load_vec(io.g_in, g);
-      lp = io.lp_in[cc];
-      ch.load_eps(0, eps);
-      ch.leapfrog(m, x, lp, g, eps, io.L);
-      ch.store_vec(io.m_out, 0, m);
-      ch.store_vec(io.x_out, 0, x);
-      ch.store_vec(io.g_out, 0, g);
-      if (grp.lane == 0) io.lp_out[cc] = lp;
-    } else {
-      ch.load_vec(p.x, x);
-      ch.load_vec(p.g, g);
-      lp = p.lp[cc];
-      unsigned long long nleap_total = 0;
-#pragma unroll 1
-      for (int t = p.t0; t < p.t1; ++t) {
-        const int r = ch.result_index(t);
-        if constexpr (MODE == kModeHMC) {
-          ch.hmc_transition(t, x, lp, g);
-          nleap_total += (unsigned long long)p.L;
-        } else {
-          typename Chain<Grp, E, Tgt>::NutsOut no;
-          ch.nuts_transition(t, x, lp, g, ckm, ckr, plan.cold_off >= 0 ? gbase + plan.cold_off : nullptr, no);
-          nleap_total += (unsigned long long)no.leapfrogs;
-          if (p.lar_last && grp.lane == 0) p.lar_last[cc] = no.log_accept_ratio;
-          if (r >= 0 && grp.lane == 0) {
-            const Trace& tr = p.tr;
-            const size_t o = (size_t)r * p.B + cc;
-            if (tr.log_accept_ratio) tr.log_accept_ratio[o] = no.log_accept_ratio;
-            if (tr.is_accepted) tr.is_accepted[o] = no.accepted ? 1 : 0;
-            if (tr.leapfrogs_taken) tr.leapfrogs_taken[o] = no.leapfrogs;
-            if (tr.has_divergence) tr.has_divergence[o] = no.has_divergence ? 1 : 0;
-            if (tr.reach_max_depth) tr.reach_max_depth[o] = no.reach_max_depth ? 1 : 0;
-            if (tr.energy) tr.energy[o] = no.energy;
-          }
-        }
-        if (r >= 0) {
-          const Trace& tr = p.tr;
-          if (tr.states) ch.store_vec(tr.states, r, x);
-          if (tr.grads) ch.store_vec(tr.grads, r, g);
-          if (grp.lane == 0) {
-            if (tr.target_log_prob) tr.target_log_prob[(size_t)r * p.B + cc] = lp;
-            if (tr.step_size && cc == 0 && p.step_kind == 0)
-              tr.step_size[r] = p.step[(size_t)t * p.step_seq_stride];
-          }
-        }
-      }
-      ch.store_vec(p.x, 0, x);
-      ch.store_vec(p.g, 0, g);
-      if (grp.lane == 0) {
-        p.lp[cc] = lp;
-        if (p.leapfrog_total) p.leapfrog_total[cc] += nleap_total;
-      }
-    }
-  }
+  chain_body<Grp, E, Tgt, MODE>(p, tp, io, plan);
 }
 
+// Host-side stand-in of the run-time-compiled UserT<WarpG, E> (pb2_user_target.cuh): same shared-memory plan, the kernel
+// itself comes from the user's build.
+template <int E>
+struct JitUserT {
+  using Params = UserParams;
+  static constexpr bool kCkptInSmem = true;
+  static size_t cta_smem_floats(const Params&) { return 0; }
+  static size_t group_smem_floats(const Params&) { return 2 * 32 * E; }
+};
+// which run-time build a target type stands for: -1 = none (offline-compiled), 0 plain, 1 ScaledT, 2 TransformedT
+template <class Tgt>
+struct JitVariant { static constexpr int value = -1; };
+template <int E>
+struct JitVariant<JitUserT<E>> { static constexpr int value = 0; };
+template <class Grp, int E>
+struct JitVariant<ScaledT<Grp, E, JitUserT<E>>> { static constexpr int value = 1; };
+template <class Grp, int E>
+struct JitVariant<TransformedT<Grp, E, JitUserT<E>>> { static constexpr int value = 2; };
+
 template <class Grp, int E, class Tgt, int MODE, int MAXT = 512>
-static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p, const PrimIO& io) {
+static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p, const PrimIO& io,
+                    const pb2_target* jit = nullptr) {
   SmemPlan plan{};
   auto r4 = [](size_t v) { return (int)((v + 3) & ~size_t(3)); };
   plan.cta_floats = r4(Tgt::cta_smem_floats(tp));
@@ -178,47 +93,72 @@ static int launch_t(pb2_ctx* ctx, const typename Tgt::Params& tp, ChainParams& p
     }
     p.ckpt_global = ctx->d_ckpt;
   }
-  auto kfn = chain_kernel<Grp, E, Tgt, MODE, MAXT>;
-  if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)smem_bytes), "cudaFuncSetAttribute"))
-    return rc;
   if (int rc = check_cuda(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(int), ctx->stream), "memset(queue)"))
     return rc;
   p.queue = ctx->d_queue;
-  kfn<<<grid, threads, smem_bytes, ctx->stream>>>(p, tp, io, plan);
+  if constexpr (JitVariant<Tgt>::value >= 0) {
+    if (!jit) return set_error(ctx, PB2_ERR_INVALID, "user target: missing target handle");
+    if (int rc = user_target_ensure(ctx, const_cast<pb2_target*>(jit), JitVariant<Tgt>::value)) return rc;
+    const void* jit_kernel = jit->user_kernels[JitVariant<Tgt>::value][MODE];
+    if (int rc = check_cuda(ctx, cudaFuncSetAttribute(jit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)smem_bytes), "cudaFuncSetAttribute(user kernel)"))
+      return rc;
+    void* args[4] = {(void*)&p, (void*)&tp, (void*)&io, (void*)&plan};
+    if (int rc = check_cuda(ctx, cudaLaunchKernel(jit_kernel, dim3(grid), dim3(threads), args, smem_bytes, ctx->stream),
+                            "user chain kernel launch"))
+      return rc;
+  } else {
+    auto kfn = chain_kernel<Grp, E, Tgt, MODE, MAXT>;
+    if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)smem_bytes), "cudaFuncSetAttribute"))
+      return rc;
+    kfn<<<grid, threads, smem_bytes, ctx->stream>>>(p, tp, io, plan);
+  }
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "chain_kernel launch");
 }
 
 template <class Grp, int E, class Tgt, int MAXT = 512>
-static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
+static int launch_mode(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io,
+                       const pb2_target* jit = nullptr) {
   switch (mode) {
-    case kModeLogpGrad: return launch_t<Grp, E, Tgt, kModeLogpGrad, MAXT>(ctx, tp, p, io);
-    case kModeLeapfrog: return launch_t<Grp, E, Tgt, kModeLeapfrog, MAXT>(ctx, tp, p, io);
-    case kModeHMC: return launch_t<Grp, E, Tgt, kModeHMC, MAXT>(ctx, tp, p, io);
-    case kModeNUTS: return launch_t<Grp, E, Tgt, kModeNUTS, MAXT>(ctx, tp, p, io);
+    case kModeLogpGrad: return launch_t<Grp, E, Tgt, kModeLogpGrad, MAXT>(ctx, tp, p, io, jit);
+    case kModeLeapfrog: return launch_t<Grp, E, Tgt, kModeLeapfrog, MAXT>(ctx, tp, p, io, jit);
+    case kModeHMC: return launch_t<Grp, E, Tgt, kModeHMC, MAXT>(ctx, tp, p, io, jit);
+    case kModeNUTS: return launch_t<Grp, E, Tgt, kModeNUTS, MAXT>(ctx, tp, p, io, jit);
   }
   return set_error(ctx, PB2_ERR_INVALID, "bad mode");
 }
 
 // the same launch with the target wrapped for diagonal preconditioning when the run carries a scale
 template <class Grp, int E, class Tgt, int MAXT = 512>
-static int launch_maybe_scaled(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io) {
+static int launch_maybe_scaled(pb2_ctx* ctx, const typename Tgt::Params& tp, int mode, ChainParams& p, const PrimIO& io,
+                              const pb2_target* jit = nullptr) {
   if (p.bij_kind) {
     using T = TransformedT<Grp, E, Tgt>;
     typename T::Params bp{tp, BijectorSpec{p.bij_kind, p.bij_lo, p.bij_hi}, p.scale, p.D};
-    return launch_mode<Grp, E, T, MAXT>(ctx, bp, mode, p, io);
+    return launch_mode<Grp, E, T, MAXT>(ctx, bp, mode, p, io, jit);
   }
-  if (!p.scale) return launch_mode<Grp, E, Tgt, MAXT>(ctx, tp, mode, p, io);
+  if (!p.scale) return launch_mode<Grp, E, Tgt, MAXT>(ctx, tp, mode, p, io, jit);
   using S = ScaledT<Grp, E, Tgt>;
   typename S::Params sp{tp, p.scale, p.D};
-  return launch_mode<Grp, E, S, MAXT>(ctx, sp, mode, p, io);
+  return launch_mode<Grp, E, S, MAXT>(ctx, sp, mode, p, io, jit);
 }
 
 int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, const PrimIO& io) {
   const int D = tgt->dim;
   if (tile_path_supported(ctx, tgt, mode, p)) return launch_tile_chain(ctx, tgt, mode, p);
   switch (tgt->kind) {
+    case PB2_TARGET_USER: {   // run-time-compiled kernels, same launcher (and the same wrappers) as the named targets
+      UserParams tp{tgt->d_a, tgt->n_rows, D};
+      switch (user_elements_per_lane(D)) {
+        case 1: return launch_maybe_scaled<WarpG, 1, JitUserT<1>>(ctx, tp, mode, p, io, tgt);
+        case 2: return launch_maybe_scaled<WarpG, 2, JitUserT<2>>(ctx, tp, mode, p, io, tgt);
+        case 4: return launch_maybe_scaled<WarpG, 4, JitUserT<4>>(ctx, tp, mode, p, io, tgt);
+        case 8: return launch_maybe_scaled<WarpG, 8, JitUserT<8>>(ctx, tp, mode, p, io, tgt);
+      }
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "user target: D > 256 not supported");
+    }
     case PB2_TARGET_EIGHT_SCHOOLS: {
       EightSchoolsParams tp{tgt->d_a, tgt->d_b, tgt->n_rows};
       return launch_maybe_scaled<WarpG, 1, EightSchoolsT<WarpG, 1>>(ctx, tp, mode, p, io);

@@ -6,7 +6,7 @@
 // return the SAME bits to every thread of the group so per-chain control flow
 // (accept / U-turn / divergence) stays uniform inside the group.
 #pragma once
-#include <cuda_runtime.h>
+#include "pb2_compat.cuh"
 
 namespace pb2 {
 

@@ -5,7 +5,10 @@
 #include <string>
 
 #include "../../include/pb2.h"
-#include "pb2_chain.cuh"
+#include <vector>
+
+#include "pb2_chain_kernel.cuh"
+#include "pb2_user_target.cuh"
 #include "pb2_targets.cuh"
 
 struct pb2_ctx {
@@ -43,24 +46,15 @@ struct pb2_target {
   float scalar = 0.f;
   unsigned char* d_tc = nullptr;   // logistic: X~ pre-split into the tensor-core operand planes (pb2_logistic_tc.cu)
   size_t tc_bytes = 0;
+  // user-defined target (pb2_user.cu): source + the loaded run-time builds, one per variant (plain / ScaledT /
+  // TransformedT, built on first use), and their kernels indexed by Mode
+  std::string user_source, user_include;
+  int user_flags = 0;
+  void* user_lib[3] = {nullptr, nullptr, nullptr};
+  void* user_kernels[3][4] = {};
 };
 
 namespace pb2 {
-
-enum Mode : int { kModeLogpGrad = 0, kModeLeapfrog = 1, kModeHMC = 2, kModeNUTS = 3 };
-
-// Extra pointers for the two primitive modes.
-struct PrimIO {
-  const float* m_in;
-  const float* x_in;
-  const float* lp_in;
-  const float* g_in;
-  float* m_out;
-  float* x_out;
-  float* lp_out;
-  float* g_out;
-  int L;
-};
 
 int set_error(pb2_ctx* ctx, int code, const std::string& msg);
 int check_cuda(pb2_ctx* ctx, cudaError_t e, const char* what);
@@ -73,6 +67,14 @@ bool tile_path_supported(const pb2_ctx* ctx, const pb2_target* tgt, int mode, co
 int launch_tile_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p);
 // pb2_tile_nuts.cu (64-chain tiles: lock-step and asynchronous-lane NUTS)
 int launch_tile_nuts(pb2_ctx* ctx, const pb2_target* tgt, ChainParams& p);
+
+// pb2_user.cu (user-defined targets: NVRTC build + load)
+int user_elements_per_lane(int dim);
+constexpr int kUserVariants = 3;
+int user_compile(pb2_ctx* ctx, const char* source, int dim, const char* include_dir, int variant, int flags,
+                 std::vector<char>& cubin);
+int user_target_ensure(pb2_ctx* ctx, pb2_target* t, int variant);
+void user_target_unload(pb2_target* t);
 
 // pb2_logistic_tc.cu
 int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g);

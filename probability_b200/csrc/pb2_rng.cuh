@@ -5,8 +5,7 @@
 // tfp/internal/backend/numpy/random_generators.py:151-158,278-302).  uint32 streams
 // are bit-exact w.r.t. that scheme; float transforms follow the same formulas.
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
+#include "pb2_compat.cuh"
 
 #define PB2_HD __host__ __device__ __forceinline__
 

@@ -38,8 +38,8 @@ struct EightSchoolsT {
   float ys, sig, logsig;
   bool active;
   int J;
-  static size_t cta_smem_floats(const Params&) { return 0; }
-  static size_t group_smem_floats(const Params&) { return 0; }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params&) { return 0; }
+  PB2_HOSTFN static size_t group_smem_floats(const Params&) { return 0; }
   __device__ void init_cta(const Params&, float*) {}
   __device__ void init_group(const Params& p, Grp& grp, float*, float*) {
     J = p.J;
@@ -98,8 +98,8 @@ struct DenseGaussianT {
   float loc[E];
   float lognorm;
   int D;
-  static size_t cta_smem_floats(const Params& p) { return (size_t)p.D * DP; }
-  static size_t group_smem_floats(const Params&) { return DP; }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params& p) { return (size_t)p.D * DP; }
+  PB2_HOSTFN static size_t group_smem_floats(const Params&) { return DP; }
   __device__ void init_cta(const Params& p, float* cta) {
     for (int i = threadIdx.x; i < p.D * DP; i += blockDim.x) {
       int r = i / DP, c = i - r * DP;
@@ -202,8 +202,8 @@ struct ScaledT {
   static constexpr bool kCkptInSmem = Tgt::kCkptInSmem;
   Tgt base;
   float sc[E];
-  static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
-  static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
+  PB2_HOSTFN static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
   __device__ void init_cta(const Params& p, float* cta) { base.init_cta(p.base, cta); }
   __device__ void init_group(const Params& p, Grp& grp, float* cta, float* gs) {
     base.init_group(p.base, grp, cta, gs);
@@ -253,8 +253,8 @@ struct TransformedT {
   Tgt base;
   float sc[E], lo[E], hi[E];
   int kind[E];
-  static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
-  static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params& p) { return Tgt::cta_smem_floats(p.base); }
+  PB2_HOSTFN static size_t group_smem_floats(const Params& p) { return Tgt::group_smem_floats(p.base); }
   __device__ void init_cta(const Params& p, float* cta) { base.init_cta(p.base, cta); }
   __device__ void init_group(const Params& p, Grp& grp, float* cta, float* gs) {
     base.init_group(p.base, grp, cta, gs);
@@ -313,8 +313,8 @@ struct LogisticT {
   const float* sX;
   const float* sy;
   int N, D;
-  static size_t cta_smem_floats(const Params& p) { return (size_t)p.N * RS + p.N; }
-  static size_t group_smem_floats(const Params&) { return 0; }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params& p) { return (size_t)p.N * RS + p.N; }
+  PB2_HOSTFN static size_t group_smem_floats(const Params&) { return 0; }
   __device__ void init_cta(const Params& p, float* cta) {
     for (int i = threadIdx.x; i < p.N * RS; i += blockDim.x) {
       int r = i / RS, c = i - r * RS;
@@ -411,8 +411,8 @@ struct StochVolT {
   float* prm;  // [8] phi, m, s, rs, lp_params
   float* wtf;  // [2*NW] forward warp totals (A,B)
   float* wtr;  // [2*NW] reverse warp totals
-  static size_t cta_smem_floats(const Params&) { return 0; }
-  static size_t group_smem_floats(const Params&) { return 8 + 4 * NW; }
+  PB2_HOSTFN static size_t cta_smem_floats(const Params&) { return 0; }
+  PB2_HOSTFN static size_t group_smem_floats(const Params&) { return 8 + 4 * NW; }
   __device__ void init_cta(const Params&, float*) {}
   __device__ void init_group(const Params& p, Grp& grp, float*, float* gs) {
     T = p.T;

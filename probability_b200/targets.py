@@ -12,6 +12,8 @@ otherwise (no CPU / autodiff fallback).
   LogisticRegression      inference_gym/targets/logistic_regression.py:42-171
   StochasticVolatility    inference_gym/targets/vectorized_stochastic_volatility.py:102-440
                           (non-centred, unconstrained space; `constrain` maps back)
+  UserTarget              any density, given as CUDA source for one chain's log-prob + gradient (compiled at run time
+                          into the same chain kernels; csrc/pb2_user_target.cuh)
 """
 import ctypes as C
 
@@ -65,6 +67,54 @@ class Target:
     from probability_b200.mcmc import _engine
     x, _, _ = _engine.flatten_state(list(state_parts))
     return self.log_prob_and_grad(x)[0]
+
+
+class UserTarget(Target):
+  """A user-defined target density: the engine's form of the reference's arbitrary `target_log_prob_fn`
+  (tfp/mcmc/hmc.py:413-415; value and gradient as in mcmc/internal/util.py:246-308).
+
+  `source` is CUDA C++ defining, for ONE chain,
+
+      __device__ float target_log_prob_and_grad(const float* x, float* g, const float* data, int n_data);
+
+  which returns log p(x) up to a constant and writes the gradient into g[0 .. dim).  It is compiled with NVRTC for
+  sm_100a into the leapfrog / HMC / NUTS chain kernels of the named targets (warp per chain), so every kernel of
+  `tfp.mcmc` -- `sample_chain`, step-size adaptation, diagnostics -- runs on it unchanged.  `data` (optional) is a flat
+  float32 array handed to every call; `part_sizes` splits the flat state into the state parts `sample_chain` sees.
+  With `cooperative=True` the function takes a trailing `int lane` and is called by all 32 lanes of the chain's warp
+  (every lane writes a disjoint part of g, all lanes return the same value; `pb2::warp_sum` is available).
+  A compile error raises `Pb2Error` carrying the compiler's log (line numbers refer to `source`)."""
+  kind = _lib.TARGET_USER
+
+  def __init__(self, dim, source, data=None, part_sizes=None, cooperative=False):
+    if not isinstance(source, str) or 'target_log_prob_and_grad' not in source:
+      raise TypeError('`source` must be CUDA source that defines target_log_prob_and_grad (see UserTarget docs)')
+    dim = int(dim)
+    if not 1 <= dim <= 256:
+      raise ValueError('UserTarget: 1 <= dim <= 256, got {}'.format(dim))
+    data = np.zeros([0], np.float32) if data is None else np.ascontiguousarray(np.asarray(data, np.float32).reshape(-1))
+    if part_sizes is not None and sum(int(n) for n in part_sizes) != dim:
+      raise ValueError('part_sizes must sum to dim')
+    self.source = source
+    self.flags = 1 if cooperative else 0   # PB2_USER_COOPERATIVE
+    super().__init__(dim=dim, n_rows=data.size, a=data, part_sizes=part_sizes)
+
+  def check(self):
+    """Compile only (no GPU needed); raises Pb2Error with the compiler's log on failure."""
+    lib = _lib.load()
+    rc = lib.pb2_user_target_check(self.source.encode(), self.dim, self.flags, _lib.CSRC_DIR.encode())
+    _lib.check(rc)
+    return True
+
+  def handle(self, ctx):
+    h = self._handles.get(ctx.device_index)
+    if h is None:
+      h = C.c_void_p()
+      data = self._a.ctypes.data_as(_lib.c_f32p) if self._a.size else None
+      _lib.check(ctx.lib.pb2_target_create_user(ctx.handle, self.dim, self.source.encode(), self.flags, data, self._a.size,
+                                                _lib.CSRC_DIR.encode(), C.byref(h)), ctx.handle)
+      self._handles[ctx.device_index] = h
+    return h
 
 
 class EightSchools(Target):
