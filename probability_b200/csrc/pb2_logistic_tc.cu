@@ -8,8 +8,13 @@
 //     D1 = z chunk [128 x 128] (TMEM)  -> epilogue: lp += y z - softplus z ; r = y - sigmoid z -> A2 = r hi/lo (TMEM)
 //     D2 += A2 [128 x K = 128 rows] . B2,  B2 = X~ chunk [n = 32 dims][k = 128 rows] K-major hi/lo (smem)
 // 3xTF32 split on both GEMMs (FP32-accurate): (3 x 4 + 3 x 16) MMAs per chunk.  TMEM: 64 + 128 + 256 + 32 = 480 columns.
+// The chunk operands (four pre-split planes, one contiguous block per chunk) are streamed by the TMA: one
+// cp.async.bulk.tensor per chunk (the plane buffer described as a 2-d tensor of 1 KB rows, box = one chunk) into a
+// 4-slot ring, completion on the slot's mbarrier, which the issuing warp waits on before the chunk's first contraction.
 // This is the primitive (SURVEY 8a row T3 on tcgen05); the transition kernels still use the FP32 warp-per-chain
 // gradient (pb2_targets.cuh LogisticT).
+#include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is resolved through the runtime at launch)
+
 #include <algorithm>
 #include "pb2_tile.cuh"
 
@@ -39,6 +44,9 @@ struct Shape {
   static constexpr int kB1Plane = R * KD * 4;   // [n = R rows][k = KD dims]
   static constexpr int kB2Plane = ND * R * 4;   // [n = ND dims][k = R rows]
   static constexpr int kChunkBytes = 2 * kB1Plane + 2 * kB2Plane;   // hi/lo of both layouts
+  static constexpr int kTmaRowBytes = 1024;                         // the TMA moves a chunk as rows of 1 KB
+  static constexpr int kChunkRows = kChunkBytes / kTmaRowBytes;
+  static_assert(kChunkBytes % kTmaRowBytes == 0 && kChunkRows <= 256, "TMA box");
   static constexpr int kTh = KD / 4;            // theta dims per worker thread
   static constexpr int kG = ND / 4;             // gradient columns per worker thread
   static constexpr int kZ = R / 4;              // logits per worker thread and chunk
@@ -127,6 +135,7 @@ __global__ void logistic_tc_prepare_kernel(const float* __restrict__ X, int N, i
 template <class S>
 struct Smem {
   unsigned long long g1_done[2], g2_done;   // mbarriers: the contraction into D1[b] / D2 has completed
+  unsigned long long full[kRing];           // mbarriers: the TMA has delivered the ring slot's operand planes
   uint32_t tmem_base;
   float y[kRing][S::R];
   float valid[kRing][S::R];
@@ -145,7 +154,7 @@ struct Smem {
 //                   partial sums part_g[segment][B][D], part_ll[segment][B] (row-sharded data: the caller reduces).
 template <class S, bool kPartial>
 __global__ void __launch_bounds__(kThreads, 1)
-logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const unsigned char* __restrict__ planes_g,
+logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const __grid_constant__ CUtensorMap planes_map,
                    const float* __restrict__ labels, int nchunks_total, int seg_chunks, float* __restrict__ out_lp,
                    float* __restrict__ out_g) {
   extern __shared__ __align__(128) unsigned char ring[];   // kRing x (B1 hi, B1 lo, B2 hi, B2 lo)
@@ -159,7 +168,9 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g1_done[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g1_done[1])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.g2_done)));
+    for (int q = 0; q < kRing; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.full[q])));
     asm volatile("fence.mbarrier_init.release.cluster;");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&planes_map) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -179,8 +190,13 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::ND >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
     uint32_t leader;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
+    unsigned nfull[kRing];   // completed waits per ring slot (-> the phase parity of its `full` barrier)
+#pragma unroll
+    for (int q = 0; q < kRing; ++q) nfull[q] = 0u;
     auto gemm1 = [&](int c) {   // z chunk = theta . X~chunk^T : 3 passes x KD/8 K-steps, M128 N=R K8
       if (!leader) return;
+      mbar_wait(smem_u32(&sh.full[c % kRing]), nfull[c % kRing] & 1u);   // the chunk's planes have landed
+      nfull[c % kRing]++;
       const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
       const uint64_t bhi = make_kmajor_desc(base, (S::R / 8) * 128, 128);
       const uint64_t blo = make_kmajor_desc(base + S::kB1Plane, (S::R / 8) * 128, 128);
@@ -226,12 +242,12 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
     };
     for (int tl = 0; tl < my_tiles; ++tl) {
       if (nchunks == 0) break;
-      asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // theta staged, chunks 0 and 1 copied
+      asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // theta staged, chunks 0 and 1 requested
       asm volatile("tcgen05.fence::after_thread_sync;");
       gemm1(0);
       if (nchunks > 1) gemm1(1);
       for (int c = 0; c < nchunks; ++c) {
-        asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // D1[c%2] read, D2 read, chunk c+2 copied
+        asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // D1[c%2] read, D2 read, chunk c+2 requested
         asm volatile("tcgen05.fence::after_thread_sync;");
         if (c + 2 < nchunks) gemm1(c + 2);
         asm volatile("bar.sync 3, %0;" ::"n"(kThreads) : "memory");   // A2[c%2] written
@@ -245,20 +261,23 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const u
     const int slice = warp >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     unsigned n1[2] = {0u, 0u}, n2 = 0u;             // completed waits per mbarrier (-> its phase parity)
-    auto stage = [&](int c) {   // chunk cbeg + c's operand planes and labels -> ring slot c % kRing (cp.async, 16 B each)
-      const unsigned char* src = planes_g + (size_t)(cbeg + c) * S::kChunkBytes;
-      const uint32_t dst = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
-      for (int i = tid; i < S::kChunkBytes / 16; i += kWorkers)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 16 * (size_t)i) : "memory");
+    auto stage = [&](int c) {   // chunk cbeg + c's operand planes (one TMA tensor copy) and labels -> ring slot c % kRing
+      if (tid == 0) {
+        const uint32_t dst = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
+        const uint32_t bar = smem_u32(&sh.full[c % kRing]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(S::kChunkBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+            "l"(&planes_map), "r"(0), "r"((cbeg + c) * S::kChunkRows), "r"(bar)
+            : "memory");
+      }
       if (tid < S::R) {
         const int n = (cbeg + c) * S::R + tid;
         sh.y[c % kRing][tid] = n < N ? labels[n] : 0.f;
         sh.valid[c % kRing][tid] = n < N ? 1.f : 0.f;
       }
     };
-    auto signal = [&](int bar) {   // workers only ARRIVE (after making their copies / generic / TMEM writes visible)
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    auto signal = [&](int bar) {   // workers only ARRIVE (after making their TMEM writes visible)
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
       if (bar == 2) asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
@@ -387,6 +406,34 @@ __global__ void logistic_tc_reduce_kernel(const float* __restrict__ part_g, cons
 }
 }  // namespace ltc
 
+// The plane buffer (nchunks blocks of S::kChunkBytes) as a 2-d float tensor of 1 KB rows; box = one chunk.
+template <class S>
+static int make_planes_map(pb2_ctx* ctx, const void* d_planes, int nchunks, CUtensorMap* map) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (int rc = check_cuda(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres),
+                            "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)"))
+      return rc;
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      return set_error(ctx, PB2_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)(S::kTmaRowBytes / 4), (cuuint64_t)std::max(nchunks, 1) * S::kChunkRows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)S::kTmaRowBytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(S::kTmaRowBytes / 4), (cuuint32_t)S::kChunkRows};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(d_planes), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ctx, PB2_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return PB2_OK;
+}
+
 int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, float* d_lp, float* d_g) {
   using namespace ltc;
   using S = SmallD;
@@ -406,7 +453,9 @@ int launch_logistic_tc(pb2_ctx* ctx, pb2_target* tgt, int B, const float* d_x, f
                           "cudaFuncSetAttribute(logistic_tc)"))
     return rc;
   const int grid = std::min((B + kM - 1) / kM, ctx->num_sms);
-  kern<<<grid, kThreads, smem, ctx->stream>>>(d_x, B, D, N, tgt->d_tc, tgt->d_b, nchunks, nchunks, d_lp, d_g);
+  CUtensorMap map;
+  if (int rc = make_planes_map<S>(ctx, tgt->d_tc, nchunks, &map)) return rc;
+  kern<<<grid, kThreads, smem, ctx->stream>>>(d_x, B, D, N, map, tgt->d_b, nchunks, nchunks, d_lp, d_g);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "logistic_tc_kernel");
 }
@@ -458,8 +507,9 @@ int launch_rowshard_tc(pb2_ctx* ctx, const unsigned char* d_planes, const float*
                           "cudaFuncSetAttribute(rowshard_tc)"))
     return rc;
   if (nchunks > 0) {
-    kern<<<dim3(ntiles, nseg), kThreads, smem, ctx->stream>>>(d_theta, B, D, N, d_planes, d_y, nchunks, seg_chunks, part_ll,
-                                                              part_g);
+    CUtensorMap map;
+    if (int rc = make_planes_map<S>(ctx, d_planes, nchunks, &map)) return rc;
+    kern<<<dim3(ntiles, nseg), kThreads, smem, ctx->stream>>>(d_theta, B, D, N, map, d_y, nchunks, seg_chunks, part_ll, part_g);
     ctx->launches += 1;
   }
   const size_t tot = (size_t)B * (D + 1);
