@@ -324,6 +324,10 @@ def run_c5(tfp, env, cpu=True, steps=10, tune=30):
   from oracle import targets as otargets
   if env.world > 1:
     assert tfp.distribute.init_comm() == env.world
+  ctx0 = tfp._lib.Context.get(env.dev)
+  collective = 'none (one rank)' if env.world == 1 else 'peer-memory reduction fused into the step kernel (CUDA IPC over NVLink)'
+  if os.environ.get('PB2_ROWSHARD_COLLECTIVE') == '0' and env.world > 1:
+    collective = 'NCCL all-reduce enqueued from C between the kernels'
   X, y = c5_shard(env.rank, env.world)
   tg = tfp.targets.RowShardedLogisticRegression(X, y)
   B, D, L = C5_B, C5_D, C5_L
@@ -360,10 +364,10 @@ def run_c5(tfp, env, cpu=True, steps=10, tune=30):
   flops = 4.0 * C5_ROWS * D * n          # all rows, all ranks
   ach = flops / dt / 1e12
   out = {'config': 'C5 logistic regression %d rows x %d weights, %d replicated chains, HMC L=%d, rows sharded over %d '
-                   'GPU(s), per-leapfrog gradient all-reduce enqueued from C' % (C5_ROWS, D, B, L, env.world),
+                   'GPU(s), per-leapfrog gradient sum over the ranks inside pb2_rowshard_leapfrog' % (C5_ROWS, D, B, L, env.world),
          'n_gpus': env.world, 'chains': B, 'steps': steps, 'value': n / dt, 'unit': UNIT, 'seconds': dt,
          'ms_per_transition': 1e3 * dt / steps, 'step_size': eps, 'accept_rate': accept, 'gpu_launches': int(launches),
-         'scaling': 'strong',
+         'scaling': 'strong', 'collective': collective,
          'roofline': {'bound': 'tensor', 'achieved': ach / env.world, 'peak': env.tf32_peak, 'unit': 'TFLOP/s',
                       'frac': ach / env.world / env.tf32_peak, 'frac_of_3xtf32_peak': ach / env.world / (env.tf32_peak / 3),
                       'note': 'per GPU; algorithmic 4*N*D = 4e8 flop per chain-gradient; includes the all-reduce and the '

@@ -91,7 +91,8 @@ long long pb2_launch_count(pb2_ctx* ctx);
  * supported -- 32 < D <= 100, B >= 256: 128-chain HMC tiles, 64-chain asynchronous-lane NUTS tiles -- else
  * warp-per-chain), 1 = force the warp-per-chain FP32-FMA kernels, 2 = half-warp-per-chain experiment,
  * 3 = tile kernels with the lock-step NUTS kernel (the reference's literal batched algorithm; the bit-exact
- * partner of the asynchronous-lane kernel in the tests). */
+ * partner of the asynchronous-lane kernel in the tests).
+ * "rowshard_collective": how pb2_rowshard_leapfrog sums the gradient over ranks, see there (default 1). */
 int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value);
 
 /* ---- targets ---------------------------------------------------------------- */
@@ -318,9 +319,13 @@ int pb2_comm_allreduce_sum(pb2_ctx* ctx, float* d_buf, long long n);
 
 /* SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-355) for the row-sharded logistic regression, all chains in
  * lock-step, ALL num_steps leapfrogs enqueued by this one call: per leapfrog the local gradient pass
- * (d_planes != NULL: tcgen05, else the FP32 kernel on d_X), the all-reduce of the packed [B, D+1] buffer over the
- * context's communicator (reduce_over_ranks != 0) and one fused kernel for prior + kick + drift.  Same argument meaning
- * as pb2_leapfrog; outputs must not alias inputs. */
+ * (d_planes != NULL: tcgen05, else the FP32 kernel on d_X), the sum of the packed [B, D+1] buffer over the ranks of the
+ * context's communicator (reduce_over_ranks != 0) and one fused kernel for prior + kick + drift.  The cross-rank sum is
+ * by default done INSIDE that fused kernel over peer memory (pb2_ctx_set_int "rowshard_collective" 1: every rank's
+ * packed buffer is mapped into every process with CUDA IPC on first use -- a collective call --, the gradient pass
+ * publishes into it, per-rank sequence flags travel over NVLink, the ranks' buffers are added in rank order so replicas
+ * stay bit-identical; single node, <= 8 ranks); "rowshard_collective" 0 enqueues an NCCL all-reduce between the two
+ * kernels instead.  Same argument meaning as pb2_leapfrog; outputs must not alias inputs. */
 int pb2_rowshard_leapfrog(pb2_ctx* ctx, const void* d_planes, const float* d_X, const float* d_y, int N, int D, int DP,
                           int B, const float* d_m, const float* d_x, const float* d_logp, const float* d_grad,
                           const float* d_step, int step_kind, int num_steps, int reduce_over_ranks, float* d_m_out,

@@ -74,6 +74,7 @@ int pb2_ctx_create(int device, pb2_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* v = getenv("PB2_DENSE_VARIANT")) c->dense_variant = atoi(v);
+  if (const char* v = getenv("PB2_ROWSHARD_COLLECTIVE")) c->rowshard_collective = atoi(v) ? 1 : 0;   // A/B runs
   if (int rc = check_cuda(c, cudaMalloc(&c->d_queue, 64), "cudaMalloc(queue)")) { delete c; return rc; }
   if (int rc = check_cuda(c, cudaMalloc(&c->d_partial, 4096), "cudaMalloc(partial)")) { delete c; return rc; }
   *out = c;
@@ -112,6 +113,11 @@ int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return PB2_ERR_INVALID;
   if (std::strcmp(name, "dense_variant") == 0) {
     ctx->dense_variant = value;
+    return PB2_OK;
+  }
+  if (std::strcmp(name, "rowshard_collective") == 0) {
+    if (value != 0 && value != 1) return set_error(ctx, PB2_ERR_INVALID, "rowshard_collective: 0 (NCCL) or 1 (peer memory)");
+    ctx->rowshard_collective = value;
     return PB2_OK;
   }
   return set_error(ctx, PB2_ERR_INVALID, std::string("pb2_ctx_set_int: unknown option ") + name);

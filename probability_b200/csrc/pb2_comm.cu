@@ -5,7 +5,12 @@
 //   * pb2_rowshard_leapfrog : SimpleLeapfrogIntegrator (tfp/mcmc/internal/leapfrog_integrator.py:280-355) for a target
 //                        whose rows are sharded over the ranks: the per-leapfrog gradient psum of
 //                        internal/distribute_lib.py:179-242, enqueued from C between the gradient kernel and the fused
-//                        prior + kick kernel -- no host code between the L leapfrogs.
+//                        prior + kick kernel -- no host code between the L leapfrogs.  By default the psum is not a
+//                        separate collective at all: every rank's packed gradient buffer is mapped into every process
+//                        (CUDA IPC over NVLink), the gradient pass publishes into it, and the fused prior + kick + drift
+//                        kernel sums the ranks' buffers itself (fixed rank order: replicas stay bit-identical), waiting on
+//                        per-rank sequence flags written over NVLink.  NCCL stays as the selectable baseline
+//                        (pb2_ctx_set_int "rowshard_collective" 0) and carries the one-time exchange of the IPC handles.
 // NCCL is bound at run time (dlopen): a process that already carries an NCCL (torch.distributed's) shares it, a plain C
 // host gets the system library.  Single-GPU users never touch it.
 #include <dlfcn.h>
@@ -13,6 +18,7 @@
 
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "pb2_internal.h"
 
@@ -94,15 +100,69 @@ __global__ void rowshard_first_kernel(int B, int D, const float* step, int step_
   x[i] = x_in[i] + eps * vv;
 }
 
+// ---- peer-memory group: rank r's buffer = [2 slots][cap floats] packed gradients + [kMaxPeers] sequence flags
+constexpr int kMaxPeers = 8;
+struct PeerView {
+  const float* data[kMaxPeers];   // every rank's buffer, mapped here (own rank: the local allocation)
+  const unsigned* flags;          // MY flags: flags[r] = last sequence number rank r has published
+  unsigned* err;                  // MY error word (set when a wait times out)
+  int n;
+  unsigned seq;                   // the sequence number this leapfrog waits for
+  size_t slot_off;                // float offset of the slot in use
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// after the gradient pass has written this rank's slot: tell every rank (one flag per peer, over NVLink)
+__global__ void peer_signal_kernel(unsigned* const* peer_flags, int n, int rank, unsigned seq) {
+  const int r = threadIdx.x;
+  if (r < n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[r] + rank), "r"(seq) : "memory");
+  }
+}
+
+template <bool kPeer>
 __global__ void rowshard_step_kernel(int last, int B, int D, const float* step, int step_kind, const float* packed,
-                                     float* v, float* x, float* grad, float* logp, float* m_out) {
+                                     const PeerView pv, float* v, float* x, float* grad, float* logp, float* m_out) {
   const int b = blockIdx.x;
+  if constexpr (kPeer) {
+    // wait until every rank has published this leapfrog's gradient (bounded: a lost peer sets the error word instead of
+    // hanging the GPU)
+    if (threadIdx.x < pv.n) {
+      long long spins = 0;
+      while ((int)(ld_acquire_sys(pv.flags + threadIdx.x) - pv.seq) < 0) {
+        if (++spins > (1ll << 23)) { atomicExch(pv.err, 1u); break; }   // seconds: far beyond any skew between ranks
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  }
+  auto summed = [&](int col) -> float {   // psum over the data axis, rank order 0 .. n-1 on every rank
+    if constexpr (kPeer) {
+      const size_t o = pv.slot_off + (size_t)b * (D + 1) + col;
+      float s = ld_relaxed_sys(pv.data[0] + o);
+      for (int r = 1; r < pv.n; ++r) s += ld_relaxed_sys(pv.data[r] + o);
+      return s;
+    } else {
+      return packed[(size_t)b * (D + 1) + col];
+    }
+  };
   float part = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const size_t i = (size_t)b * D + d;
     const float eps = step_kind == 0 ? step[0] : (step_kind == 1 ? step[d] : step[b]);
     const float t = x[i];
-    const float gn = -t + packed[(size_t)b * (D + 1) + d];
+    const float gn = -t + summed(d);
     grad[i] = gn;
     part += -0.5f * t * t - kHalfLog2Pi;
     const float vv = v[i] + eps * gn;
@@ -117,8 +177,102 @@ __global__ void rowshard_step_kernel(int last, int B, int D, const float* step, 
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sh[k];
-    logp[b] = s + packed[(size_t)b * (D + 1) + D];
+    logp[b] = s + summed(D);
   }
+}
+
+struct PeerGroup {
+  int n = 0, rank = 0;
+  size_t cap = 0;                       // floats per slot
+  unsigned char* local = nullptr;       // [2][cap] floats | flags [kMaxPeers] | error word
+  float* data[kMaxPeers] = {};          // mapped base pointers of every rank's allocation
+  unsigned** d_peer_flags = nullptr;    // device array [n]: every rank's flag array (for peer_signal_kernel)
+  unsigned seq = 0;
+  unsigned* h_err = nullptr;            // pinned mirror of the error word, refreshed after every call
+  cudaEvent_t err_ready = nullptr;      // (reserved)
+  size_t bytes() const { return 2 * cap * sizeof(float) + (kMaxPeers + 1) * sizeof(unsigned); }
+  unsigned* flags_of(int r) const { return reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(data[r]) + 2 * cap * sizeof(float)); }
+};
+
+// every rank has finished the kernels it enqueued before this point (a peer may still be reading my buffer)
+static void peer_barrier(pb2_ctx* ctx) {
+  NcclApi* api = nccl_api();
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(float)) != cudaSuccess) return;
+  cudaMemsetAsync(d, 0, sizeof(float), ctx->stream);
+  api->AllReduce(d, d, 1, ncclFloat32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+}
+
+static void peer_destroy(pb2_ctx* ctx) {
+  PeerGroup* g = static_cast<PeerGroup*>(ctx->peer);
+  if (!g) return;
+  if (g->n > 1 && g->data[g->n - 1]) peer_barrier(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (g->h_err) cudaFreeHost(g->h_err);
+  if (g->err_ready) cudaEventDestroy(g->err_ready);
+  for (int r = 0; r < g->n; ++r)
+    if (r != g->rank && g->data[r]) cudaIpcCloseMemHandle(g->data[r]);
+  cudaFree(g->local);
+  cudaFree(g->d_peer_flags);
+  delete g;
+  ctx->peer = nullptr;
+}
+
+// Collective over the communicator: (re)build the peer group with room for `floats` per slot.
+static int peer_ensure(pb2_ctx* ctx, size_t floats) {
+  PeerGroup* g = static_cast<PeerGroup*>(ctx->peer);
+  if (g && g->cap >= floats) return PB2_OK;
+  if (ctx->comm_size > kMaxPeers)
+    return set_error(ctx, PB2_ERR_UNSUPPORTED, "peer-memory reduction: at most 8 ranks (pb2_ctx_set_int rowshard_collective 0)");
+  peer_destroy(ctx);
+  NcclApi* api = nccl_api();
+  g = new PeerGroup();
+  g->n = ctx->comm_size;
+  g->rank = ctx->comm_rank;
+  g->cap = (floats + 1023) & ~(size_t)1023;
+  int rc = check_cuda(ctx, cudaMalloc((void**)&g->local, g->bytes()), "cudaMalloc(peer buffer)");
+  if (!rc) rc = check_cuda(ctx, cudaMemsetAsync(g->local, 0, g->bytes(), ctx->stream), "memset(peer buffer)");
+  cudaIpcMemHandle_t mine;
+  if (!rc) rc = check_cuda(ctx, cudaIpcGetMemHandle(&mine, g->local), "cudaIpcGetMemHandle");
+  unsigned char* d_h = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(g->n);
+  if (!rc) rc = check_cuda(ctx, cudaMalloc((void**)&d_h, sizeof(mine) * (g->n + 1)), "cudaMalloc(ipc handles)");
+  if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream), "memcpy(ipc handle)");
+  if (!rc)
+    rc = check_nccl(ctx, api, api->AllGather(d_h, d_h + sizeof(mine), sizeof(mine), ncclUint8, (ncclComm_t)ctx->comm, ctx->stream),
+                    "ncclAllGather(ipc handles)");
+  if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(all.data(), d_h + sizeof(mine), sizeof(mine) * g->n, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(ipc handles)");
+  if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync(ipc handles)");
+  cudaFree(d_h);
+  for (int r = 0; r < g->n && !rc; ++r) {
+    if (r == g->rank) { g->data[r] = reinterpret_cast<float*>(g->local); continue; }
+    void* p = nullptr;
+    rc = check_cuda(ctx, cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer access over NVLink)");
+    g->data[r] = static_cast<float*>(p);
+  }
+  if (!rc) {
+    unsigned* fl[kMaxPeers] = {};
+    for (int r = 0; r < g->n; ++r) fl[r] = g->flags_of(r);
+    rc = check_cuda(ctx, cudaMalloc((void**)&g->d_peer_flags, sizeof(fl)), "cudaMalloc(peer flag table)");
+    if (!rc) rc = check_cuda(ctx, cudaMemcpy(g->d_peer_flags, fl, sizeof(fl), cudaMemcpyHostToDevice), "memcpy(peer flag table)");
+  }
+  if (!rc) rc = check_cuda(ctx, cudaMallocHost((void**)&g->h_err, sizeof(unsigned)), "cudaMallocHost(peer error word)");
+  if (!rc) {
+    *g->h_err = 0;
+    rc = check_cuda(ctx, cudaEventCreateWithFlags(&g->err_ready, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  ctx->peer = g;
+  if (rc) { peer_destroy(ctx); return rc; }
+  return PB2_OK;
+}
+
+// a wait that timed out in an earlier call (a peer that never published) is reported by the next call / by destroy
+static int peer_check(pb2_ctx* ctx, PeerGroup* g) {
+  if (g && g->h_err && *(volatile unsigned*)g->h_err)
+    return set_error(ctx, PB2_ERR_CUDA, "pb2_rowshard_leapfrog: timed out waiting for a peer's gradient in an earlier call");
+  return PB2_OK;
 }
 
 }  // namespace pb2
@@ -161,10 +315,17 @@ int pb2_comm_destroy(pb2_ctx* ctx) {
   NcclApi* api = nccl_api();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  int prc = PB2_OK;
+  if (ctx->peer) {
+    cudaStreamSynchronize(ctx->stream);
+    prc = peer_check(ctx, static_cast<PeerGroup*>(ctx->peer));
+  }
+  peer_destroy(ctx);
   ncclResult_t r = api->CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
   ctx->comm_size = 1;
   ctx->comm_rank = 0;
+  if (prc) return prc;
   return check_nccl(ctx, api, r, "ncclCommDestroy");
 }
 
@@ -199,19 +360,51 @@ int pb2_rowshard_leapfrog(pb2_ctx* ctx, const void* d_planes, const float* d_X, 
   }
   float* v = ctx->d_rs;
   float* packed = v + nBD;
+  const size_t npk = (size_t)B * (D + 1);
+  const bool peer = reduce_over_ranks && ctx->rowshard_collective == 1 && ctx->comm_size > 1;
+  PeerGroup* g = nullptr;
+  if (peer) {
+    if (int rc = peer_ensure(ctx, npk)) return rc;
+    g = static_cast<PeerGroup*>(ctx->peer);
+    if (int rc = peer_check(ctx, g)) return rc;
+  }
   const unsigned nb = (unsigned)((nBD + 255) / 256);
   rowshard_first_kernel<<<nb, 256, 0, ctx->stream>>>(B, D, d_step, step_kind, d_m, d_grad, d_x, v, d_x_out);
   ctx->launches += 1;
   for (int l = 0; l < num_steps; ++l) {
-    int rc = d_planes ? pb2_rowshard_logistic_grad_tc(ctx, d_planes, d_y, N, D, d_x_out, B, packed)
-                      : pb2_rowshard_logistic_grad(ctx, d_X, d_y, N, D, DP, d_x_out, B, packed);
+    PeerView pv{};
+    float* dst = packed;
+    if (peer) {   // this leapfrog's slot of my peer buffer: the gradient pass publishes straight into it
+      g->seq += 1;
+      pv.n = g->n;
+      pv.seq = g->seq;
+      pv.slot_off = (size_t)(g->seq & 1u) * g->cap;
+      for (int r = 0; r < g->n; ++r) pv.data[r] = g->data[r];
+      pv.flags = g->flags_of(g->rank);
+      pv.err = g->flags_of(g->rank) + kMaxPeers;
+      dst = g->data[g->rank] + pv.slot_off;
+    }
+    int rc = d_planes ? pb2_rowshard_logistic_grad_tc(ctx, d_planes, d_y, N, D, d_x_out, B, dst)
+                      : pb2_rowshard_logistic_grad(ctx, d_X, d_y, N, D, DP, d_x_out, B, dst);
     if (rc) return rc;
-    if (reduce_over_ranks)   // psum over the data axis
-      if (int rc2 = comm_allreduce_sum(ctx, packed, (size_t)B * (D + 1))) return rc2;
-    rowshard_step_kernel<<<B, 128, 0, ctx->stream>>>(l + 1 == num_steps ? 1 : 0, B, D, d_step, step_kind, packed, v,
-                                                     d_x_out, d_grad_out, d_logp_out, d_m_out);
-    ctx->launches += 1;
+    const int last = l + 1 == num_steps ? 1 : 0;
+    if (peer) {
+      peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(g->d_peer_flags, g->n, g->rank, g->seq);
+      rowshard_step_kernel<true><<<B, 128, 0, ctx->stream>>>(last, B, D, d_step, step_kind, nullptr, pv, v, d_x_out, d_grad_out,
+                                                             d_logp_out, d_m_out);
+      ctx->launches += 2;
+    } else {
+      if (reduce_over_ranks)   // psum over the data axis as a separate collective
+        if (int rc2 = comm_allreduce_sum(ctx, packed, npk)) return rc2;
+      rowshard_step_kernel<false><<<B, 128, 0, ctx->stream>>>(last, B, D, d_step, step_kind, packed, pv, v, d_x_out, d_grad_out,
+                                                              d_logp_out, d_m_out);
+      ctx->launches += 1;
+    }
   }
+  if (peer)   // refresh the host mirror of the error word (stream-ordered, no host synchronisation)
+    if (int rc = check_cuda(ctx, cudaMemcpyAsync(g->h_err, g->flags_of(g->rank) + kMaxPeers, sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, ctx->stream), "memcpy(peer error word)"))
+      return rc;
   return check_cuda(ctx, cudaGetLastError(), "pb2_rowshard_leapfrog kernels");
 }
 

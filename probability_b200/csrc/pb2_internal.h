@@ -34,6 +34,10 @@ struct pb2_ctx {
   int comm_rank = 0, comm_size = 1;
   float* d_rs = nullptr;           // row-sharded leapfrog scratch: v [B, D] + packed [B, D + 1]
   size_t rs_bytes = 0;
+  // peer-memory group of the row-sharded leapfrog (pb2_comm.cu PeerGroup): every rank's packed gradient buffer mapped
+  // into every process (CUDA IPC), so the cross-rank sum is done by the consuming kernel itself
+  void* peer = nullptr;
+  int rowshard_collective = 1;     // 0: NCCL all-reduce between the kernels; 1: peer-memory reduction in the step kernel
 };
 
 struct pb2_target {

@@ -500,7 +500,10 @@ int launch_rowshard_tc(pb2_ctx* ctx, const unsigned char* d_planes, const float*
   }
   float* part_g = reinterpret_cast<float*>(ctx->d_sched);
   float* part_ll = part_g + (size_t)nseg * B * D;
-  if (int rc = check_cuda(ctx, cudaMemsetAsync(part_g, 0, pneed, ctx->stream), "memset(rowshard partials)")) return rc;
+  // every (tile, segment) CTA overwrites its whole block of the partials (all segments hold >= 1 chunk); only an empty
+  // shard leaves them untouched
+  if (nchunks == 0)
+    if (int rc = check_cuda(ctx, cudaMemsetAsync(part_g, 0, pneed, ctx->stream), "memset(rowshard partials)")) return rc;
   const size_t smem = (size_t)kRing * S::kChunkBytes;
   auto kern = logistic_tc_kernel<S, true>;
   if (int rc = check_cuda(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

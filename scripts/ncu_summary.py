@@ -33,7 +33,12 @@ def main():
   rep, out = sys.argv[1], sys.argv[2]
   txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
   rows = list(csv.reader(txt.splitlines()))
-  hdr, units, vals = rows[0], rows[1], rows[2]
+  hdr, units = rows[0], rows[1]
+  # several launches in the report: summarise the longest one
+  dur = hdr.index('gpu__time_duration.sum')
+  tosec = {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}
+  vals = max(rows[2:], key=lambda r: float(r[dur].replace(',', '')) if len(r) > dur and r[dur] else 0.0)
+  del tosec
   name = vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''
   with open(out, 'w') as f:
     f.write('# %s\n# kernel: %s\nmetric,unit,value\n' % (rep, name))

@@ -1,6 +1,7 @@
 """Run under torchrun on >= 2 GPUs (one process per GPU, NCCL), once with the collectives issued from Python
-(torch.distributed) and once with the library-owned communicator (tfp.distribute.init_comm: fused sharded dual
-averaging inside pb2_run, per-leapfrog all-reduce inside pb2_rowshard_leapfrog):
+(torch.distributed) and twice with the library-owned communicator (tfp.distribute.init_comm: fused sharded dual
+averaging inside pb2_run; the per-leapfrog gradient sum inside pb2_rowshard_leapfrog once as an NCCL all-reduce between
+the kernels and once as the peer-memory reduction fused into the step kernel):
   (a) chain-sharded NUTS + DualAveraging == the unsharded run (global-chain-index RNG counters, cross-rank
       log-mean-exp): same step sizes on every rank, same states bit for bit;
   (b) row-sharded logistic HMC with the per-leapfrog gradient all-reduce == all rows on one GPU, and all
@@ -24,13 +25,16 @@ def main():
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   dist.init_process_group('nccl', device_id=dev)
-  for mode in ('torch.distributed collectives', 'library-owned communicator'):
+  ctx = tfp._lib.Context.get(dev)
+  for mode in ('torch.distributed collectives', 'library-owned communicator, NCCL all-reduce between the kernels',
+               'library-owned communicator, peer-memory reduction inside the step kernel'):
     if mode.startswith('library'):
       assert tfp.distribute.init_comm() == world
       assert tfp.distribute.comm_size() == world
       t = torch.full((5,), float(rank + 1), device=dev)
       tfp.distribute.all_reduce_sum(t)
       assert torch.equal(t, torch.full((5,), world * (world + 1) / 2.0, device=dev))
+      ctx.set_int('rowshard_collective', 1 if 'peer-memory' in mode else 0)
     check(rank, world, dev, mode)
   dist.barrier()
   if rank == 0:
