@@ -301,6 +301,15 @@ int pb2_rowshard_logistic_finish(pb2_ctx* ctx, const float* d_packed, const floa
 int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_step, int step_kind,
                           float* d_v, float* d_x, const float* d_g, const float* d_m_in, float* d_m_out);
 
+/* SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-355) for the logistic-regression target (D <= 32) with all chains
+ * in lock-step on the tensor cores: every leapfrog's log-prob + gradient is one launch of the tcgen05 kernel behind
+ * pb2_logistic_logp_grad_tc, with one fused kick + drift kernel between them; all num_steps leapfrogs are enqueued by
+ * this call.  Same argument meaning as pb2_leapfrog; outputs must not alias inputs.  (The transition path of
+ * HamiltonianMonteCarlo on this target for large batches: a fixed L makes lock-step free of waste.) */
+int pb2_logistic_tc_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, const float* d_x,
+                             const float* d_logp, const float* d_grad, const float* d_step, int step_kind, int num_steps,
+                             float* d_m_out, float* d_x_out, float* d_logp_out, float* d_grad_out);
+
 /* ---- multi-GPU group ------------------------------------------------------------------------
  * One NCCL communicator per context (one process per GPU).  Replaces the named-axis collectives of
  * internal/distribute_lib.py:147-242 (psum / reduce_logsumexp / pbroadcast) on this path:

