@@ -61,17 +61,20 @@ PB2_HD uint32_t philox4x32_10_word(uint32_t k0, uint32_t k1, uint32_t c0, uint32
   return w == 0 ? c0 : (w == 1 ? c1 : (w == 2 ? c2 : c3));
 }
 
+// out of line: keeps the 10 Philox rounds out of the callers' instruction stream (register allocation of the tile kernels)
+__host__ __device__ __noinline__ inline uint32_t philox_bits_at(Key k, uint64_t idx) {
+  const uint64_t blk = idx >> 2;
+  return philox4x32_10_word(k.k0, k.k1, (uint32_t)blk, (uint32_t)(blk >> 32), (int)(idx & 3));
+}
+
 // Element `idx` of a flat draw of `n` uint32 (row-major over the requested shape).
 PB2_HD uint32_t bits_at(Key k, uint64_t idx, uint64_t n, int layout) {
   uint32_t o0, o1;
-  if (layout == kLayoutPhilox) {
-    const uint64_t blk = idx >> 2;
-    return philox4x32_10_word(k.k0, k.k1, (uint32_t)blk, (uint32_t)(blk >> 32), (int)(idx & 3));
-  }
-  if (layout == kLayoutPartitionable) {
+  if (layout == kLayoutPartitionable) {   // the default first: the hot kernels draw through this function
     threefry2x32(k.k0, k.k1, (uint32_t)(idx >> 32), (uint32_t)idx, o0, o1);
     return o0 ^ o1;
   }
+  if (layout == kLayoutPhilox) return philox_bits_at(k, idx);
   const uint64_t half = (n + 1) >> 1;  // counters iota(n) padded to even, split in halves
   if (idx < half) {
     uint64_t c1 = half + idx;
