@@ -92,7 +92,10 @@ long long pb2_launch_count(pb2_ctx* ctx);
  * warp-per-chain), 1 = force the warp-per-chain FP32-FMA kernels, 2 = half-warp-per-chain experiment,
  * 3 = tile kernels with the lock-step NUTS kernel (the reference's literal batched algorithm; the bit-exact
  * partner of the asynchronous-lane kernel in the tests).
- * "rowshard_collective": how pb2_rowshard_leapfrog sums the gradient over ranks, see there (default 1). */
+ * "rowshard_collective": how pb2_rowshard_leapfrog sums the gradient over ranks, see there (default 1).
+ * "synchronous_run": 1 = pb2_run waits for the stream before it returns; default 0 = all work is enqueued on the context's
+ * stream and the call returns (host outputs -- the pass-along seed, the step seeds -- are final on return; device outputs
+ * are stream-ordered). */
 int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value);
 
 /* ---- targets ---------------------------------------------------------------- */

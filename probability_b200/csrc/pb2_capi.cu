@@ -92,6 +92,8 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
   cudaFree(ctx->d_sched);
   cudaFree(ctx->d_step_keys);
   cudaFree(ctx->d_step_seq);
+  if (ctx->h_keys) cudaFreeHost(ctx->h_keys);
+  if (ctx->keys_copied) cudaEventDestroy(ctx->keys_copied);
   delete ctx;
   return PB2_OK;
 }
@@ -113,6 +115,10 @@ int pb2_ctx_set_int(pb2_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return PB2_ERR_INVALID;
   if (std::strcmp(name, "dense_variant") == 0) {
     ctx->dense_variant = value;
+    return PB2_OK;
+  }
+  if (std::strcmp(name, "synchronous_run") == 0) {
+    ctx->synchronous_run = value ? 1 : 0;
     return PB2_OK;
   }
   if (std::strcmp(name, "rowshard_collective") == 0) {
@@ -477,7 +483,21 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
     const int T = t_end - t;
     if (int rc = ensure(ctx, (void**)&ctx->d_step_keys, &ctx->step_keys_bytes, sizeof(uint32_t) * 2 * (size_t)T, "cudaMalloc(step keys)")) return rc;
     if (int rc = ensure(ctx, (void**)&ctx->d_sched, &ctx->sched_bytes, sizeof(uint32_t) * (size_t)stride * T, "cudaMalloc(key schedule)")) return rc;
-    if (int rc = check_cuda(ctx, cudaMemcpyAsync(ctx->d_step_keys, keys.data() + 2 * (size_t)t, sizeof(uint32_t) * 2 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream), "memcpy(step keys)")) return rc;
+    // the seeds go through pinned memory owned by the context, so that the copy may outlive this call
+    const size_t kbytes = sizeof(uint32_t) * 2 * (size_t)T;
+    if (ctx->keys_copied) cudaEventSynchronize(ctx->keys_copied);   // an earlier call's copy has left the staging buffer
+    if (kbytes > ctx->h_keys_bytes) {
+      if (ctx->h_keys) cudaFreeHost(ctx->h_keys);
+      ctx->h_keys = nullptr;
+      ctx->h_keys_bytes = 0;
+      if (int rc = check_cuda(ctx, cudaMallocHost((void**)&ctx->h_keys, kbytes), "cudaMallocHost(step keys)")) return rc;
+      ctx->h_keys_bytes = kbytes;
+    }
+    if (!ctx->keys_copied)
+      if (int rc = check_cuda(ctx, cudaEventCreateWithFlags(&ctx->keys_copied, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    std::memcpy(ctx->h_keys, keys.data() + 2 * (size_t)t, kbytes);
+    if (int rc = check_cuda(ctx, cudaMemcpyAsync(ctx->d_step_keys, ctx->h_keys, kbytes, cudaMemcpyHostToDevice, ctx->stream), "memcpy(step keys)")) return rc;
+    if (int rc = check_cuda(ctx, cudaEventRecord(ctx->keys_copied, ctx->stream), "cudaEventRecord")) return rc;
     int rc = nuts ? launch_nuts_sched(ctx, ctx->d_step_keys, T, lay->n_parts, cfg->max_tree_depth, lay->rng_layout, ctx->d_sched)
                   : launch_hmc_sched(ctx, ctx->d_step_keys, T, lay->n_parts, lay->rng_layout, ctx->d_sched);
     if (rc) return rc;
@@ -522,8 +542,9 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
     if (!rc) rc = launch_scale_rows(ctx, p.tr.final_momentum, R, p.D, p.scale, 1);
     if (rc) return rc;
   }
-  // `keys` (pageable host memory) must outlive the async copy
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync(run)");
+  // everything above is enqueued on the context's stream; the caller's later work on that stream is ordered after it
+  if (ctx->synchronous_run) return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync(run)");
+  return check_cuda(ctx, cudaGetLastError(), "pb2_run");
 }
 
 // ------------------------------------------------------------------ dual averaging

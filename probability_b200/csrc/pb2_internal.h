@@ -18,6 +18,10 @@ struct pb2_ctx {
   int max_smem_optin = 227 * 1024;
   long long launches = 0;
   int dense_variant = 0;           // A/B switch of the dense-Gaussian kernels, see pb2_ctx_set_int in pb2.h
+  int synchronous_run = 0;         // 1: pb2_run waits for the stream before returning (default: enqueue and return)
+  uint32_t* h_keys = nullptr;      // pinned staging of the per-transition seeds (the H2D copy outlives pb2_run)
+  size_t h_keys_bytes = 0;
+  cudaEvent_t keys_copied = nullptr;
   std::string err;
   int* d_queue = nullptr;          // dynamic chain queue counter
   float* d_ckpt = nullptr;         // global checkpoint scratch (block-group targets)
