@@ -323,7 +323,7 @@ int pb2_logistic_tc_leapfrog(pb2_ctx* ctx, const pb2_target* tgt, int B, const f
 #define PB2_COMM_ID_BYTES 128
 int pb2_comm_unique_id(void* out_id /* PB2_COMM_ID_BYTES host bytes */);
 int pb2_comm_init(pb2_ctx* ctx, int nranks, int rank, const void* nccl_unique_id);
-int pb2_comm_destroy(pb2_ctx* ctx);
+int pb2_comm_destroy(pb2_ctx* ctx);   /* collective (all ranks call it): closes the peer-memory mappings behind a barrier */
 int pb2_comm_size(pb2_ctx* ctx);   /* 1 without a communicator */
 int pb2_comm_rank(pb2_ctx* ctx);
 /* in-place sum over the ranks, enqueued on the context's stream (parity surface of the collective) */
