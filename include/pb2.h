@@ -59,6 +59,11 @@ extern "C" {
 #define PB2_TARGET_STOCH_VOL 3
 #define PB2_TARGET_STOCH_VOL_CONSTRAINED 4 /* the same model in its own coordinates [persistence, mean, scale, z] */
 #define PB2_TARGET_USER 5 /* user-defined: CUDA source compiled at run time, see pb2_target_create_user */
+/* the CENTRED stochastic-volatility model (inference_gym/targets/stochastic_volatility.py:39-111): one latent
+ * log-volatility per time step, state [phi, m, s, x[T]]; 6 = unconstrained coordinates with the Sigmoid(-1,1) / Softplus
+ * bijectors folded in, 7 = the model's own coordinates (for a TransformedTransitionKernel) */
+#define PB2_TARGET_STOCH_VOL_CENTERED 6
+#define PB2_TARGET_STOCH_VOL_CENTERED_CONSTRAINED 7
 
 /* elementwise event-space bijectors (one per state dimension), tfp/bijectors/{identity,exp,softplus,sigmoid}.py */
 #define PB2_BIJECTOR_IDENTITY 0

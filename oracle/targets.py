@@ -193,6 +193,70 @@ class StochasticVolatility:
     return lp.astype(dt), g.astype(dt)
 
 
+class StochasticVolatilityCentered:
+  """CENTRED stochastic volatility: one latent log-volatility x_t per time step,
+  inference_gym/targets/stochastic_volatility.py:39-52 (AR(1) prior x_0 ~ N(m, s / sqrt(1 - phi^2)),
+  x_t ~ N(m + phi (x_{t-1} - m), s)), :68-90 (priors: 2 Beta(20, 1.5) - 1, Cauchy(0, 5), HalfCauchy(0, 2)),
+  :102-111 (y_t ~ N(0, exp(x_t / 2))).  Same posterior as the non-centred model, its gradient is a 3-point stencil.
+  State layout [phi, m, s, x_0..x_{T-1}]; `folded=True`: unconstrained coordinates u = [u_phi, m, u_s, x] with the
+  Sigmoid(-1, 1) / Softplus bijectors and their forward-log-det-Jacobians folded in (transformed_kernel.py:86-140)."""
+
+  def __init__(self, centered_returns, dtype=np.float32, folded=True):
+    self.dtype = dtype
+    self.y = np.asarray(centered_returns, dtype)
+    self.T = self.y.size
+    self.dim = self.T + 3
+    self.part_sizes = [1, 1, 1, self.T]
+    self.folded = folded
+
+  def logp_grad(self, u):
+    dt = self.dtype
+    u = np.asarray(u, dt)
+    u1, m, u3, x = u[:, 0], u[:, 1], u[:, 2], u[:, 3:]
+    if self.folded:
+      sg, sgm = _sigmoid(u1), _sigmoid(-u1)
+      phi = dt(2) * sg - dt(1)
+      s = _softplus(u3)
+    else:
+      phi, s = u1, u3
+    q = np.sqrt(dt(1) - phi * phi)
+    d = x - m[:, None]
+    e = np.empty_like(x)
+    e[:, 0] = d[:, 0] * q / s
+    e[:, 1:] = (d[:, 1:] - phi[:, None] * d[:, :-1]) / s[:, None]
+    y2e = (self.y[None, :] ** 2) * np.exp(-x)
+    lp_x = np.sum(dt(-0.5) * e * e - dt(_HALF_LOG_2PI) - np.log(s)[:, None], axis=1) + np.log(q)
+    lik = np.sum(dt(-0.5) * y2e - dt(_HALF_LOG_2PI) - dt(0.5) * x, axis=1)
+    b = (phi + dt(1)) * dt(0.5)
+    from math import lgamma
+    lbeta = lgamma(20.0) + lgamma(1.5) - lgamma(21.5)
+    lp_phi = dt(19.0) * np.log(b) + dt(0.5) * np.log1p(-b) - dt(lbeta) - dt(np.log(2.0))
+    lp_m = -dt(np.log(np.pi * 5.0)) - np.log1p((m / dt(5)) ** 2)
+    lp_s = dt(np.log(2.0)) - dt(np.log(np.pi * 2.0)) - np.log1p((s / dt(2)) ** 2)
+    lp = lik + lp_x + lp_phi + lp_m + lp_s
+    g = np.empty_like(u)
+    c = np.ones_like(x)
+    c[:, 0] = q
+    gx = -e * c / s[:, None] + dt(0.5) * (y2e - dt(1))
+    gx[:, :-1] += e[:, 1:] * (phi / s)[:, None]
+    g[:, 3:] = gx
+    cm = np.full_like(x, dt(1)) * (dt(1) - phi)[:, None]
+    cm[:, 0] = q
+    d_m = np.sum(e * cm, axis=1) / s - (dt(2) * m / dt(25)) / (dt(1) + (m / dt(5)) ** 2)
+    d_s = np.sum(e * e - dt(1), axis=1) / s - (s / dt(2)) / (dt(1) + (s / dt(2)) ** 2)
+    d_phi = (np.sum(e[:, 1:] * d[:, :-1], axis=1) / s + e[:, 0] * d[:, 0] * phi / (s * q) - phi / (q * q)
+             + dt(0.5) * (dt(19.0) / b - dt(0.5) / (dt(1) - b)))
+    if self.folded:
+      lp = lp + (dt(np.log(2.0)) - _softplus(-u1) - _softplus(u1)) + (-_softplus(-u3))
+      g[:, 0] = d_phi * (dt(2) * sg * sgm) + (sgm - sg)
+      g[:, 2] = d_s * _sigmoid(u3) + _sigmoid(-u3)
+    else:
+      g[:, 0] = d_phi
+      g[:, 2] = d_s
+    g[:, 1] = d_m
+    return lp.astype(dt), g.astype(dt)
+
+
 def synthetic_sv_returns(T=2516, phi=0.95, s=0.25, m=None, seed=0):
   """Synthetic S&P500-shape centred returns simulated from the model itself
   (SURVEY section 8d, C4)."""

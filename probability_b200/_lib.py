@@ -20,6 +20,7 @@ LAYOUT_PHILOX = 2
 TARGET_EIGHT_SCHOOLS, TARGET_DENSE_GAUSSIAN, TARGET_LOGISTIC, TARGET_STOCH_VOL = 0, 1, 2, 3
 TARGET_STOCH_VOL_CONSTRAINED = 4
 TARGET_USER = 5
+TARGET_STOCH_VOL_CENTERED, TARGET_STOCH_VOL_CENTERED_CONSTRAINED = 6, 7
 CSRC_DIR = os.path.join(_HERE, 'csrc')   # the device headers a user-defined target is compiled against (NVRTC)
 KERNEL_HMC, KERNEL_NUTS = 0, 1
 STEP_SCALAR, STEP_PER_DIM, STEP_PER_CHAIN = 0, 1, 2

@@ -153,6 +153,8 @@ int pb2_target_create(pb2_ctx* ctx, const pb2_target_desc* d, pb2_target** out) 
       break;
     case PB2_TARGET_STOCH_VOL:
     case PB2_TARGET_STOCH_VOL_CONSTRAINED:
+    case PB2_TARGET_STOCH_VOL_CENTERED:
+    case PB2_TARGET_STOCH_VOL_CENTERED_CONSTRAINED:
       if (d->n_rows < 1 || d->dim != d->n_rows + 3 || d->dim > 2560)
         return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: need dim == T + 3 <= 2560");
       na = d->n_rows;

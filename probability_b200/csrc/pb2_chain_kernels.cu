@@ -197,6 +197,17 @@ int launch_chain(pb2_ctx* ctx, const pb2_target* tgt, int mode, ChainParams& p, 
       if (D <= 5 * 512) return launch_maybe_scaled<BlockG<16>, 5, StochVolT<BlockG<16>, 5>>(ctx, tp, mode, p, io);
       return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
     }
+    case PB2_TARGET_STOCH_VOL_CENTERED: {
+      StochVolParams tp{tgt->d_a, tgt->n_rows};
+      if (D <= 5 * 512) return launch_maybe_scaled<BlockG<16>, 5, StochVolCenteredT<BlockG<16>, 5>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
+    }
+    case PB2_TARGET_STOCH_VOL_CENTERED_CONSTRAINED: {
+      StochVolParams tp{tgt->d_a, tgt->n_rows};
+      if (D <= 5 * 512)
+        return launch_maybe_scaled<BlockG<16>, 5, StochVolCenteredT<BlockG<16>, 5, false>>(ctx, tp, mode, p, io);
+      return set_error(ctx, PB2_ERR_UNSUPPORTED, "stochastic volatility: T > 2557 not supported");
+    }
   }
   return set_error(ctx, PB2_ERR_INVALID, "unknown target kind");
 }

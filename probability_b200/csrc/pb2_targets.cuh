@@ -575,4 +575,121 @@ struct StochVolT {
   }
 };
 
+// --------------------------------------------------------------------------
+// CENTRED stochastic volatility (inference_gym/targets/stochastic_volatility.py:39-52,68-111): one latent
+// log-volatility x_t per time step, x_0 ~ N(m, s / sqrt(1 - phi^2)), x_t ~ N(m + phi (x_{t-1} - m), s),
+// y_t ~ N(0, exp(x_t / 2)), the same priors on phi, m, s as the non-centred model above.  No scan: with the residuals
+//   e_0 = (x_0 - m) q / s,  e_t = ((x_t - m) - phi (x_{t-1} - m)) / s,  q = sqrt(1 - phi^2),
+// the gradient is a 3-point stencil, d/dx_t = -e_t c_t / s + phi e_{t+1} / s + (y_t^2 e^{-x_t} - 1) / 2 (c_0 = q, else 1),
+// and the three parameter derivatives are sums over t.  Same CTA-per-chain mapping as StochVolT: state [phi, m, s, x],
+// thread `lane` owns elements lane E .. lane E + E - 1, its neighbours' boundary values come by shuffle (and through
+// shared memory across warps).  kFolded as above.
+template <class Grp, int E, bool kFolded = true>
+struct StochVolCenteredT {
+  static_assert(Grp::kIsBlock && E >= 4, "stochastic volatility runs CTA-per-chain");
+  using Params = StochVolParams;
+  static constexpr bool kCkptInSmem = false;
+  static constexpr int NW = Grp::G / 32;
+  float ysq[E];
+  int T;
+  float* prm;  // [8] phi, m, s, q, lp_params
+  float* wb;   // [2*NW] warp boundary values: last x of warp w | first residual of warp w
+  PB2_HOSTFN static size_t cta_smem_floats(const Params&) { return 0; }
+  PB2_HOSTFN static size_t group_smem_floats(const Params&) { return 8 + 2 * NW; }
+  __device__ void init_cta(const Params&, float*) {}
+  __device__ void init_group(const Params& p, Grp& grp, float*, float* gs) {
+    T = p.T;
+    prm = gs;
+    wb = gs + 8;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      int tau = grp.lane * E + j - 3;
+      float yv = (tau >= 0 && tau < T) ? p.y[tau] : 0.f;
+      ysq[j] = yv * yv;
+    }
+  }
+  __device__ float logp_grad(Grp& grp, const float (&x)[E], float (&g)[E]) {
+    const int lane = grp.lane, wl = lane & 31, w = lane >> 5;
+    float sg = 0.f, sgm = 0.f, sg3 = 0.f, sgm3 = 0.f;
+    if (lane == 0) {
+      const float u1 = x[0], mm = x[1], u3 = x[2];
+      sg = sigmoidf(u1); sgm = sigmoidf(-u1);
+      sg3 = sigmoidf(u3); sgm3 = sigmoidf(-u3);
+      const float phi0 = kFolded ? 2.f * sg - 1.f : u1;
+      const float s0 = kFolded ? softplusf(u3) : u3;
+      const float b = (phi0 + 1.f) * 0.5f;
+      const float lp_phi = 19.f * logf(b) + 0.5f * log1pf(-b) - (-4.63282391111f) - 0.693147180559945f;
+      const float m5 = mm / 5.f;
+      const float lp_m = -2.75416779828f - log1pf(m5 * m5);           // -log(pi*5)
+      const float s2 = s0 * 0.5f;
+      const float lp_s = 0.693147180559945f - 1.83787706640935f - log1pf(s2 * s2);  // log2 - log(2 pi)
+      const float fldj = kFolded ? (0.693147180559945f - softplusf(-u1) - softplusf(u1)) + (-softplusf(-u3)) : 0.f;
+      const float q0 = sqrtf(1.f - phi0 * phi0);
+      prm[0] = phi0; prm[1] = mm; prm[2] = s0; prm[3] = q0;
+      prm[4] = lp_phi + lp_m + lp_s + fldj + logf(q0);               // + log q: the x_0 term's -log(s / q)
+    }
+    // the x before my first element: the previous thread's last one
+    float xprev = __shfl_up_sync(0xffffffffu, x[E - 1], 1);
+    if (wl == 31) wb[w] = x[E - 1];
+    __syncthreads();
+    if (wl == 0) xprev = w > 0 ? wb[w - 1] : 0.f;
+    const float phi = prm[0], m = prm[1], s = prm[2], q = prm[3], lp_params = prm[4];
+    const float rs_ = 1.f / s, logs = logf(s);
+    float e[E];
+    float s_lp = 0.f, s_m = 0.f, s_s = 0.f, s_phi = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int tau = lane * E + j - 3;
+      float ev = 0.f;
+      if (tau >= 0 && tau < T) {
+        const float d = x[j] - m;
+        const float dp = (j > 0 ? x[j > 0 ? j - 1 : 0] : xprev) - m;
+        if (tau == 0) {
+          ev = d * q * rs_;
+          s_m = fmaf(ev, q, s_m);
+          s_phi = fmaf(ev * d, phi / q, s_phi);
+        } else {
+          ev = (d - phi * dp) * rs_;
+          s_m = fmaf(ev, 1.f - phi, s_m);
+          s_phi = fmaf(ev, dp, s_phi);
+        }
+        s_s += ev * ev - 1.f;
+        const float y2e = ysq[j] * expf(-x[j]);
+        s_lp += (-0.5f * ev * ev - kHalfLog2Pi - logs) + (-0.5f * y2e - kHalfLog2Pi - 0.5f * x[j]);
+        g[j] = 0.5f * (y2e - 1.f);   // the likelihood part; the stencil is added below
+      } else {
+        g[j] = 0.f;
+      }
+      e[j] = ev;
+    }
+    // the residual after my last element: the next thread's first one
+    float enext = __shfl_down_sync(0xffffffffu, e[0], 1);
+    if (wl == 0) wb[NW + w] = e[0];
+    __syncthreads();
+    if (wl == 31) enext = w + 1 < NW ? wb[NW + w + 1] : 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int tau = lane * E + j - 3;
+      if (tau >= 0 && tau < T) {
+        const float en = j + 1 < E ? e[j + 1 < E ? j + 1 : 0] : enext;   // 0 past the end of the series
+        const float c = tau == 0 ? q : 1.f;
+        g[j] += (phi * en - e[j] * c) * rs_;
+      }
+    }
+    float sums[4] = {s_lp, s_m, s_s, s_phi};
+    grp.template sumN<4>(sums);
+    if (lane == 0) {
+      const float b = (phi + 1.f) * 0.5f;
+      const float m5 = m / 5.f, s2 = s * 0.5f;
+      const float d_m = sums[1] * rs_ - (2.f * m / 25.f) / (1.f + m5 * m5);
+      const float d_s = sums[2] * rs_ - s2 / (1.f + s2 * s2);
+      const float d_phi = sums[3] * rs_ - phi / (q * q) + 0.5f * (19.f / b - 0.5f / (1.f - b));
+      g[0] = kFolded ? d_phi * (2.f * sg * sgm) + (sgm - sg) : d_phi;
+      g[1] = d_m;
+      g[2] = kFolded ? d_s * sg3 + sgm3 : d_s;
+    }
+    return sums[0] + lp_params;
+  }
+};
+
 }  // namespace pb2

@@ -12,6 +12,7 @@ otherwise (no CPU / autodiff fallback).
   LogisticRegression      inference_gym/targets/logistic_regression.py:42-171
   StochasticVolatility    inference_gym/targets/vectorized_stochastic_volatility.py:102-440
                           (non-centred, unconstrained space; `constrain` maps back)
+  StochasticVolatilityCentered   inference_gym/targets/stochastic_volatility.py:39-111 (one latent per time step)
   UserTarget              any density, given as CUDA source for one chain's log-prob + gradient (compiled at run time
                           into the same chain kernels; csrc/pb2_user_target.cuh)
 """
@@ -253,6 +254,28 @@ class StochasticVolatilityConstrained(Target):
     """vectorized_stochastic_volatility.py:346-356."""
     from probability_b200 import bijectors as b
     return [b.Sigmoid(-1., 1.), b.Identity(), b.Softplus(), b.Identity()]
+
+
+class StochasticVolatilityCentered(Target):
+  """The CENTRED stochastic-volatility model (inference_gym/targets/stochastic_volatility.py:39-111): one latent
+  log-volatility x_t per time step -- x_0 ~ N(m, s / sqrt(1 - phi^2)), x_t ~ N(m + phi (x_{t-1} - m), s),
+  y_t ~ N(0, exp(x_t / 2)) -- in unconstrained coordinates [logit-ish persistence, mean_log_volatility,
+  softplus^-1 shock scale, log_volatility[T]].  Same posterior as `StochasticVolatility` (the non-centred form), a
+  harder geometry; its gradient is a 3-point stencil."""
+  kind = _lib.TARGET_STOCH_VOL_CENTERED
+  constrain = staticmethod(StochasticVolatility.constrain)
+
+  def __init__(self, centered_returns):
+    y = np.asarray(centered_returns, np.float32)
+    self.centered_returns = y
+    super().__init__(dim=y.size + 3, n_rows=y.size, a=y, part_sizes=[1, 1, 1, y.size])
+
+
+class StochasticVolatilityCenteredConstrained(StochasticVolatilityCentered):
+  """The centred model in its own coordinates [persistence in (-1, 1), mean, shock scale > 0, log_volatility[T]]; sample it
+  through `TransformedTransitionKernel(kernel, default_event_space_bijector())`."""
+  kind = _lib.TARGET_STOCH_VOL_CENTERED_CONSTRAINED
+  default_event_space_bijector = staticmethod(StochasticVolatilityConstrained.default_event_space_bijector)
 
 
 class RowShardedLogisticRegression(Target):
