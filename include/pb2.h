@@ -309,6 +309,19 @@ int pb2_rowshard_logistic_finish(pb2_ctx* ctx, const float* d_packed, const floa
 int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_step, int step_kind,
                           float* d_v, float* d_x, const float* d_g, const float* d_m_in, float* d_m_out);
 
+/* The Metropolis-Hastings step of a lock-step HMC transition as ONE kernel: log_acceptance_correction
+ * = 1/2 (sum m0^2 - sum m1^2) (hmc.py:862-875), log_accept_ratio = safe_sum(lp1, -lp0, correction)
+ * (metropolis_hastings.py:204-215, util.py:205-235), u ~ uniform at counter chain_offset + b of a [B_global] draw under
+ * accept_key, accept iff log u < ratio (:221-227), and mcmc_util.choose (util.py:103-164) of the state and of every
+ * per-chain field of the results (d_prev_*: the previous accepted results' momenta and correction).  Outputs must not
+ * alias inputs. */
+int pb2_hmc_mh_finish(pb2_ctx* ctx, int B, int D, int B_global, int chain_offset, int rng_layout,
+                      const uint32_t accept_key[2], const float* d_m0, const float* d_m1, const float* d_x0,
+                      const float* d_lp0, const float* d_g0, const float* d_x1, const float* d_lp1, const float* d_g1,
+                      const float* d_prev_m0, const float* d_prev_m1, const float* d_prev_corr, float* d_x_out,
+                      float* d_lp_out, float* d_g_out, float* d_m0_out, float* d_m1_out, float* d_corr_acc_out,
+                      float* d_corr, float* d_log_accept_ratio, unsigned char* d_is_accepted);
+
 /* SimpleLeapfrogIntegrator (leapfrog_integrator.py:280-355) for the logistic-regression target (D <= 32) with all chains
  * in lock-step on the tensor cores: every leapfrog's log-prob + gradient is one launch of the tcgen05 kernel behind
  * pb2_logistic_logp_grad_tc, with one fused kick + drift kernel between them; all num_steps leapfrogs are enqueued by

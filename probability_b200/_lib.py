@@ -123,6 +123,7 @@ def load():
         'pb2_rowshard_tc_prepare': ([vp, vp, i32, i32, i32, vp], i32),
         'pb2_rowshard_logistic_grad_tc': ([vp, vp, vp, i32, i32, vp, i32, vp], i32),
         'pb2_rowshard_logistic_finish': ([vp, vp, vp, i32, i32, vp, vp], i32),
+        'pb2_hmc_mh_finish': ([vp, i32, i32, i32, i32, i32, c_u32p] + [vp] * 20, i32),
         'pb2_logistic_tc_leapfrog': ([vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp], i32),
         'pb2_lockstep_leapfrog': ([vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp], i32),
         'pb2_comm_unique_id': ([vp], i32),

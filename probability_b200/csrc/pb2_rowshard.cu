@@ -161,6 +161,58 @@ __global__ void lockstep_leapfrog_kernel(int mode, int B, int D, const float* st
   }
 }
 
+
+// ---- Metropolis-Hastings step of a lock-step HMC transition, one kernel: log_acceptance_correction
+// (hmc.py:862-875), log_accept_ratio with safe_sum (metropolis_hastings.py:204-215, util.py:205-235), the uniform draw at
+// counter = global chain index, accept iff log u < ratio (:221-227), and mcmc_util.choose (util.py:103-164) of the state
+// and of every per-chain field of the kernel results.  One block per chain.
+struct MhFinishArgs {
+  int B, D, chain_offset, layout;
+  unsigned long long B_global;
+  Key key;
+  const float *m0, *m1, *x0, *lp0, *g0, *x1, *lp1, *g1, *pm0, *pm1, *pcorr;
+  float *x_out, *lp_out, *g_out, *m0_out, *m1_out, *corr_acc, *corr, *ratio;
+  unsigned char* accepted;
+};
+
+__global__ void mh_finish_kernel(const MhFinishArgs a) {
+  const int b = blockIdx.x;
+  const size_t row = (size_t)b * a.D;
+  float s0 = 0.f, s1 = 0.f;
+  for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+    const float u = a.m0[row + d], v = a.m1[row + d];
+    s0 = fmaf(u, u, s0);
+    s1 = fmaf(v, v, s1);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  __shared__ float sh[2][4];
+  __shared__ int acc_s;
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s0; sh[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float k0 = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]), k1 = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+    const float corr = 0.5f * finite_or_neginf(k0 + (-k1));
+    const float ratio = finite_or_neginf((a.lp1[b] + (-a.lp0[b])) + corr);
+    const float u = uniform_from_bits(bits_at(a.key, (uint64_t)a.chain_offset + (uint64_t)b, a.B_global, a.layout), 0.f, 1.f);
+    const bool acc = logf(u) < ratio;
+    a.corr[b] = corr;
+    a.ratio[b] = ratio;
+    a.accepted[b] = acc ? 1 : 0;
+    a.lp_out[b] = acc ? a.lp1[b] : a.lp0[b];
+    a.corr_acc[b] = acc ? corr : a.pcorr[b];
+    acc_s = acc ? 1 : 0;
+  }
+  __syncthreads();
+  const bool acc = acc_s != 0;
+  for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+    a.x_out[row + d] = acc ? a.x1[row + d] : a.x0[row + d];
+    a.g_out[row + d] = acc ? a.g1[row + d] : a.g0[row + d];
+    a.m0_out[row + d] = acc ? a.m0[row + d] : a.pm0[row + d];
+    a.m1_out[row + d] = acc ? a.m1[row + d] : a.pm1[row + d];
+  }
+}
+
 }  // namespace pb2
 
 using namespace pb2;
@@ -224,6 +276,26 @@ int pb2_lockstep_leapfrog(pb2_ctx* ctx, int mode, int B, int D, const float* d_s
                                                                                d_x, d_g, d_m_in, d_m_out);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "lockstep_leapfrog_kernel");
+}
+
+int pb2_hmc_mh_finish(pb2_ctx* ctx, int B, int D, int B_global, int chain_offset, int rng_layout,
+                      const uint32_t accept_key[2], const float* d_m0, const float* d_m1, const float* d_x0,
+                      const float* d_lp0, const float* d_g0, const float* d_x1, const float* d_lp1, const float* d_g1,
+                      const float* d_prev_m0, const float* d_prev_m1, const float* d_prev_corr, float* d_x_out,
+                      float* d_lp_out, float* d_g_out, float* d_m0_out, float* d_m1_out, float* d_corr_acc_out,
+                      float* d_corr, float* d_log_accept_ratio, unsigned char* d_is_accepted) {
+  if (!ctx || B < 1 || D < 1 || B_global < B || chain_offset < 0 || !accept_key || !d_m0 || !d_m1 || !d_x0 || !d_lp0 ||
+      !d_g0 || !d_x1 || !d_lp1 || !d_g1 || !d_prev_m0 || !d_prev_m1 || !d_prev_corr || !d_x_out || !d_lp_out || !d_g_out ||
+      !d_m0_out || !d_m1_out || !d_corr_acc_out || !d_corr || !d_log_accept_ratio || !d_is_accepted ||
+      rng_layout < PB2_LAYOUT_PARTITIONABLE || rng_layout > PB2_LAYOUT_PHILOX)
+    return set_error(ctx, PB2_ERR_INVALID, "pb2_hmc_mh_finish: bad argument");
+  cudaSetDevice(ctx->device);
+  MhFinishArgs a{B, D, chain_offset, rng_layout, (unsigned long long)B_global, Key{accept_key[0], accept_key[1]},
+                 d_m0, d_m1, d_x0, d_lp0, d_g0, d_x1, d_lp1, d_g1, d_prev_m0, d_prev_m1, d_prev_corr,
+                 d_x_out, d_lp_out, d_g_out, d_m0_out, d_m1_out, d_corr_acc_out, d_corr, d_log_accept_ratio, d_is_accepted};
+  mh_finish_kernel<<<B, 128, 0, ctx->stream>>>(a);
+  ctx->launches += 1;
+  return check_cuda(ctx, cudaGetLastError(), "mh_finish_kernel");
 }
 
 }  // extern "C"

@@ -243,7 +243,7 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
   def one_step(self, current_state, previous_kernel_results, seed=None):
     pkr = previous_kernel_results
     if self._lockstep:   # MetropolisHastings(UncalibratedHMC) over the lock-step leapfrog
-      return self._impl.one_step(current_state, pkr, seed=seed)
+      return self._lockstep_one_step(current_state, pkr, seed)
     seed = pb_random.sanitize_seed(seed)
     x, shapes, was_list = _engine.flatten_state(current_state)
     x = x.clone()
@@ -272,6 +272,59 @@ class HamiltonianMonteCarlo(kernel_base.TransitionKernel):
         proposed_state=_engine.unflatten(out['proposed_state'][0], shapes, was_list),
         proposed_results=proposed, extra=[], seed=seed)
     return _engine.unflatten(x, shapes, was_list), results
+
+  def _lockstep_one_step(self, current_state, pkr, seed):
+    """Lock-step targets (row-sharded data, tensor-core logistic): the same transition as
+    MetropolisHastings(UncalibratedHMC).one_step -- identical seeds and draws -- in three C-ABI calls: momentum draw,
+    all L leapfrogs (the target's lock-step integrator), and ONE kernel for the Metropolis-Hastings step
+    (pb2_hmc_mh_finish: correction, ratio, uniform, accept, choose of every field)."""
+    import torch
+    if type(self) is not HamiltonianMonteCarlo or self.chain_shard is not None:
+      return self._impl.one_step(current_state, pkr, seed=seed)   # preconditioned / sharded variants: composed path
+    seed = pb_random.sanitize_seed(seed)
+    proposal_seed, acceptance_seed = pb_random.split_seed(seed)           # metropolis_hastings.py:183
+    acc = pkr.accepted_results
+    x, shapes, was_list = _engine.flatten_state(current_state)
+    x = x.contiguous()
+    B, D = x.shape
+    g = _engine.flatten_state(list(acc.grads_target_log_prob))[0].contiguous()
+    lp = acc.target_log_prob.contiguous()
+    step_size, L = self._step_and_L(pkr)
+    step, step_kind = _engine.step_size_tensor(step_size, B, D, shapes, x.device)
+    sizes = _engine.part_sizes_of(shapes)
+    seeds = pb_random.split_seed(proposal_seed, n=len(sizes))             # hmc.py:685
+    m0 = torch.cat([pb_random.normal((B, n), seed=seeds[i], device=x.device) for i, n in enumerate(sizes)],
+                   dim=1).contiguous()                                    # hmc.py:689-695
+    m1, x1, lp1, g1 = self._target.leapfrog(m0, x, lp, g, step, step_kind, L)
+    pm0 = _engine.flatten_state(acc.initial_momentum)[0].contiguous()
+    pm1 = _engine.flatten_state(acc.final_momentum)[0].contiguous()
+    pcorr = acc.log_acceptance_correction.contiguous()
+    x_out, g_out, m0_out, m1_out = (torch.empty_like(x) for _ in range(4))
+    lp_out, corr_acc, corr, ratio = (torch.empty_like(lp) for _ in range(4))
+    is_acc = torch.empty(B, dtype=torch.uint8, device=x.device)
+    ctx = _lib.Context.get(x.device)
+    ctx.bind_stream()
+    key = np.ascontiguousarray(acceptance_seed, np.uint32)
+    _lib.check(ctx.lib.pb2_hmc_mh_finish(
+        ctx.handle, B, D, B, 0, pb_random.default_layout(), _lib.u32p(key), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(x),
+        _lib.ptr(lp), _lib.ptr(g), _lib.ptr(x1), _lib.ptr(lp1), _lib.ptr(g1), _lib.ptr(pm0), _lib.ptr(pm1),
+        _lib.ptr(pcorr), _lib.ptr(x_out), _lib.ptr(lp_out), _lib.ptr(g_out), _lib.ptr(m0_out), _lib.ptr(m1_out),
+        _lib.ptr(corr_acc), _lib.ptr(corr), _lib.ptr(ratio), _lib.ptr(is_acc)), ctx.handle)
+    is_acc = is_acc.bool()
+    proposed = acc._replace(
+        log_acceptance_correction=corr, target_log_prob=lp1,
+        grads_target_log_prob=_engine.unflatten(g1, shapes, True),
+        initial_momentum=_engine.unflatten(m0, shapes, was_list),
+        final_momentum=_engine.unflatten(m1, shapes, was_list), seed=proposal_seed)
+    accepted = acc._replace(
+        log_acceptance_correction=corr_acc, target_log_prob=lp_out,
+        grads_target_log_prob=_engine.unflatten(g_out, shapes, True),
+        initial_momentum=_engine.unflatten(m0_out, shapes, was_list),
+        final_momentum=_engine.unflatten(m1_out, shapes, was_list), seed=[])
+    results = MetropolisHastingsKernelResults(
+        accepted_results=accepted, is_accepted=is_acc, log_accept_ratio=ratio,
+        proposed_state=_engine.unflatten(x1, shapes, was_list), proposed_results=proposed, extra=[], seed=seed)
+    return _engine.unflatten(x_out, shapes, was_list), results
 
   # ---- fused multi-transition driver used by sample_chain ------------------
   _FUSED_FIELDS = {
