@@ -15,6 +15,9 @@
 namespace pb2 {
 using namespace tile64;
 
+constexpr int kColS4 = kColD + kNP;   // TMEM columns 320 .. 423: the 4-leaf-subtree checkpoint (m | rho per slice)
+static_assert(kColS4 + kSlices * 2 * kK <= 512, "TMEM budget");
+
 #ifdef PB2_TILE_PROF
 __device__ unsigned long long g_tile_prof[2][16];
 struct Prof {
@@ -161,6 +164,12 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
   const bool odd = (i & 1) != 0;
   const int ones = __ffs(~i) - 1;          // trailing ones: the leaf closes subtrees of 2, 4, .., 2^ones leaves
   const bool slot1 = odd && ones >= 2;     // (tile-uniform) the 4-leaf subtree closes: its checkpoint is slot pc - 2
+  // The checkpoint of a 4-leaf subtree's first leaf (i % 4 == 0) is read back three leaves later: it lives in the free
+  // TMEM columns of the thread's own lane (26 columns per slice: m | rho) instead of the L2 scratch, which only keeps the
+  // first leaves of the 8-, 16-, 32-leaf subtrees (i % 8 == 0).  TMEM accesses are warp-collective: they sit outside the
+  // per-lane `act` branches (an inactive lane parks garbage in its own columns).
+  const bool s4_store = !odd && (i & 3) == 0;
+  const uint32_t s4_addr = cx.lane_addr + kColS4 + 2 * kK * cx.slice;
   if (act) {
 #pragma unroll
     for (int j = 0; j < kK; ++j) {
@@ -171,7 +180,7 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
     if (!odd) {
       seg_stv(e.ckl, cl, m);
       seg_stv(e.ckl + kVS, cl, rho);
-      if ((i & 3) == 0) {   // an even leaf that is checked again after leaf i + 1
+      if ((i & 7) == 0) {   // the first leaf of an 8-leaf (or larger) subtree: checked again after leaf i + 3
         seg_stv(e.ck_m + (size_t)pc * kVS, cl, m);
         seg_stv(e.ck_r + (size_t)pc * kVS, cl, rho);
       }
@@ -180,6 +189,22 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
         seg_stv(e.hi_r + (size_t)hi_slot_w * kVS, cl, rho);
       }
     }
+  }
+  auto s4_st = [&](uint32_t a, const float (&v)[kK]) {   // 13 columns straight from the registers
+    tmem_st<8>(a, reinterpret_cast<const uint32_t(&)[8]>(v[0]));
+    tmem_st<4>(a + 8, reinterpret_cast<const uint32_t(&)[4]>(v[8]));
+    tmem_st<1>(a + 12, reinterpret_cast<const uint32_t(&)[1]>(v[12]));
+  };
+  auto s4_ld = [&](uint32_t a, float (&v)[kK]) {
+    tmem_ld<8>(a, reinterpret_cast<uint32_t(&)[8]>(v[0]));
+    tmem_ld<4>(a + 8, reinterpret_cast<uint32_t(&)[4]>(v[8]));
+    tmem_ld<1>(a + 12, reinterpret_cast<uint32_t(&)[1]>(v[12]));
+  };
+  if (s4_store) {
+    s4_st(s4_addr, m);
+    s4_st(s4_addr + kK, rho);
+  }
+  if (act) {
 #pragma unroll
     for (int j = 0; j < kK; ++j) rho[j] = rho[j] + m[j];
     if (odd) {
@@ -192,15 +217,19 @@ __device__ __forceinline__ bool nuts_leaf(Ctx& cx, const LeafEnv& e, int i, unsi
         s6[2] = fmaf(diff, km[j], s6[2]);
         s6[3] = fmaf(diff, m[j], s6[3]);
       }
-      if (slot1) {   // same reduction: one barrier less on every fourth leaf
-        seg_ldv(e.ck_m + (size_t)(pc - 2) * kVS, cl, km);
-        seg_ldv(e.ck_r + (size_t)(pc - 2) * kVS, cl, kr);
+    }
+  }
+  if (slot1) {   // same reduction as the 2-leaf check: one barrier less on every fourth leaf
+    float km[kK], kr[kK];
+    s4_ld(s4_addr, km);
+    s4_ld(s4_addr + kK, kr);
+    tmem_wait_ld();
+    if (act) {
 #pragma unroll
-        for (int j = 0; j < kK; ++j) {
-          const float diff = rho[j] - kr[j];
-          s6[4] = fmaf(diff, km[j], s6[4]);
-          s6[5] = fmaf(diff, m[j], s6[5]);
-        }
+      for (int j = 0; j < kK; ++j) {
+        const float diff = rho[j] - kr[j];
+        s6[4] = fmaf(diff, km[j], s6[4]);
+        s6[5] = fmaf(diff, m[j], s6[5]);
       }
     }
   }
