@@ -13,8 +13,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
   python bench.py --steps 20 --warmup 5 --no-ess --no-cpu-baseline --configs none > $O/launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tile_nuts_async_kernel -s 156 -c 1 -o $O/tile_nuts_async \
   python bench.py --steps 20 --warmup 5 --no-ess --no-cpu-baseline --configs none > $O/tile_nuts_async.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 2 -c 1 -o $O/nuts_sv \
-  env PROBE_NOADAPT=1 python scripts/probe_perf.py c4 > $O/nuts_sv.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 3 -c 2 -o $O/nuts_sv \
+  python scripts/ncu_sv_nuts.py > $O/nuts_sv.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:logistic_tc_kernel -s 2 -c 1 -o $O/rowshard_tc \
   python scripts/perf_rowshard.py > $O/rowshard_tc.log 2>&1
 compute-sanitizer --tool memcheck python scripts/sanitize_small.py > $O/sanitizer_memcheck.log 2>&1
