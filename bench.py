@@ -26,8 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of tile_nuts_async_kernel per NUTS transition of 16,384 chains (ncu, r01)
-NCU_DRAM_BYTES_PER_TRANSITION = 6.4e8
+# dram__bytes_read.sum + dram__bytes_write.sum of tile_nuts_async_kernel per NUTS transition of 16,384 chains: the r02 ncu
+# capture of a timed 20-transition launch (0.91 GB read + 9.68 GB written) / 20
+NCU_DRAM_BYTES_PER_TRANSITION = 5.3e8
 METRIC = 'leapfrog_grad_evals_per_sec'
 UNIT = 'grad-evals/s'
 D = 100
@@ -424,11 +425,11 @@ def main():
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
               'frac_of_3xtf32_peak': achieved / (peak / 3.0),   # FP32-accurate split: 3 tensor-core passes per flop
               'traffic': NCU_DRAM_BYTES_PER_TRANSITION * args.steps,
-              'traffic_source': 'ncu --set full of this kernel (profiles/r01_tile_nuts_async_ncu_full_summary.csv): '
+              'traffic_source': 'ncu --set full of this kernel (profiles/r02_tile_nuts_async_ncu_full_summary.csv): '
                                 'dram read+write bytes per transition of 16,384 chains, scaled to the K of this launch',
               'peak_source': pk_src + ': 0.5 x bf16_tflops_sustained (dense TF32)',
               'kernel': 'tile_nuts_async_kernel (tcgen05 kind::tf32; 3xTF32 split x 112/100 padding x two half-rows per '
-                        'chain: the tensor pipe executes ~7x the algorithmic flops; ncu: tensor pipe 18.6 % active; the '
+                        'chain: the tensor pipe executes ~7x the algorithmic flops; ncu: tensor pipe 20 % active; the '
                         'kernel is bound by the dependent latency of one leapfrog, DESIGN.md section 5)'}
   cpu_baseline = None
   if not args.no_cpu_baseline and world == 1:

@@ -351,7 +351,7 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
             float* d_step_size, const pb2_da* da, const pb2_trace* trace, unsigned long long* d_leapfrog_total) {
   if (!ctx || !tgt || !lay || !cfg || !h_seed || !d_x || !d_logp || !d_grad || !d_step_size)
     return set_error(ctx, PB2_ERR_INVALID, "pb2_run: NULL argument");
-  if (lay->B < 0 || lay->B_global < lay->B || lay->chain_offset < 0 || lay->chain_offset + lay->B > lay->B_global)
+  if (lay->B < 1 || lay->B_global < lay->B || lay->chain_offset < 0 || lay->chain_offset + lay->B > lay->B_global)
     return set_error(ctx, PB2_ERR_INVALID, "pb2_run: inconsistent chain layout");
   if (lay->rng_layout < PB2_LAYOUT_PARTITIONABLE || lay->rng_layout > PB2_LAYOUT_PHILOX)
     return set_error(ctx, PB2_ERR_INVALID, "pb2_run: unknown generator layout");
