@@ -370,8 +370,8 @@ def run_c5(tfp, env, cpu=True, steps=10, tune=30):
          'scaling': 'strong', 'collective': collective,
          'roofline': {'bound': 'tensor', 'achieved': ach / env.world, 'peak': env.tf32_peak, 'unit': 'TFLOP/s',
                       'frac': ach / env.world / env.tf32_peak, 'frac_of_3xtf32_peak': ach / env.world / (env.tf32_peak / 3),
-                      'note': 'per GPU; algorithmic 4*N*D = 4e8 flop per chain-gradient; includes the all-reduce and the '
-                              'host-driven Metropolis step between the L-leapfrog calls'}}
+                      'note': 'per GPU; algorithmic 4*N*D = 4e8 flop per chain-gradient; the timed transition includes the momentum '
+                              'draw, the cross-rank gradient sum of every leapfrog and the Metropolis-Hastings kernel'}}
   # min-ESS/s: a short run of draws (every transition is ~ms: bounded)
   nd = 24
   draws = []
