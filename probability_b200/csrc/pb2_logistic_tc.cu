@@ -143,10 +143,11 @@ struct Smem {
 };
 
 // Software pipeline (per 128-chain tile, chunk c of R rows of X~):
-//   workers : start the async copy of chunk c+2's operands -> wait z(c) -> read it (D1[c%2] is free) -> take the g
-//             chunk of c-1 out of D2 -> signal A -> sigmoid / softplus of my logits -> r hi/lo into A2[c%2] -> signal B
+//   workers : start the async copy of chunk c+2's operands -> wait z(c) -> read it (D1[c%2] is free) -> sigmoid /
+//             softplus of my logits -> wait for GEMM 2 of c-1 (take the g group out of D2) -> signal A -> r hi/lo into
+//             A2[c%2] -> signal B
 //   issuer  : on A: GEMM 1 of chunk c+2 into D1[c%2];  on B: GEMM 2 of chunk c into D2
-// so both contractions run in the shadow of the workers' transcendental work.  UTCHMMA issue is back-pressured by
+// so GEMM 1 of c+2 and GEMM 2 of c run back to back in the shadow of the workers' transcendental work on chunk c+1.  UTCHMMA issue is back-pressured by
 // the tensor pipe, which is why it lives in a warp of its own.  Signals A / B are named barriers 2 / 3 on which the
 // workers only arrive.
 // kPartial = false: one CTA runs whole tiles over ALL rows and writes log-prob and gradient (prior included).
@@ -190,13 +191,11 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const _
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::ND >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
     uint32_t leader;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
-    unsigned nfull[kRing];   // completed waits per ring slot (-> the phase parity of its `full` barrier)
-#pragma unroll
-    for (int q = 0; q < kRing; ++q) nfull[q] = 0u;
+    uint32_t full_parity = 0u;   // bit q: phase parity of ring slot q's `full` barrier (a register, not an indexed array)
     auto gemm1 = [&](int c) {   // z chunk = theta . X~chunk^T : 3 passes x KD/8 K-steps, M128 N=R K8
       if (!leader) return;
-      mbar_wait(smem_u32(&sh.full[c % kRing]), nfull[c % kRing] & 1u);   // the chunk's planes have landed
-      nfull[c % kRing]++;
+      mbar_wait(smem_u32(&sh.full[c % kRing]), (full_parity >> (c % kRing)) & 1u);   // the chunk's planes have landed
+      full_parity ^= 1u << (c % kRing);
       const uint32_t base = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
       const uint64_t bhi = make_kmajor_desc(base, (S::R / 8) * 128, 128);
       const uint64_t blo = make_kmajor_desc(base + S::kB1Plane, (S::R / 8) * 128, 128);
@@ -260,7 +259,7 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const _
     const int row = 32 * (warp & 3) + (tid & 31);   // chain of the tile = TMEM lane
     const int slice = warp >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    unsigned n1[2] = {0u, 0u}, n2 = 0u;             // completed waits per mbarrier (-> its phase parity)
+    uint32_t g1_parity = 0u, n2 = 0u;               // bit b: phase parity of g1_done[b]; n2: completed g2_done waits
     auto stage = [&](int c) {   // chunk cbeg + c's operand planes (one TMA tensor copy) and labels -> ring slot c % kRing
       if (tid == 0) {
         const uint32_t dst = smem_u32(ring + (size_t)(c % kRing) * S::kChunkBytes);
@@ -325,16 +324,14 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const _
       for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
         if (c + 2 < nchunks) stage(c + 2);   // slot (c+2) % 4 was last read by chunk c-2's contractions (waited for)
-        mbar_wait(smem_u32(&sh.g1_done[b]), n1[b] & 1u);
-        n1[b]++;
+        mbar_wait(smem_u32(&sh.g1_done[b]), (g1_parity >> b) & 1u);
+        g1_parity ^= 1u << b;
         asm volatile("tcgen05.fence::after_thread_sync;");
         uint32_t zq[S::kZ];
         tmem_ld_n<S::kZ>(lane_addr + S::kColD1 + S::R * b + S::kZ * slice, zq);
         tmem_wait_ld();
-        // chunk c-1's contraction 2 is the last reader of A2[(c-1)%2] and the writer of D2
-        if (c >= 1) take_g(c % S::kGroup == 0);
-        signal(2);
-        // ---- my logits -> log-likelihood terms, r = y - sigmoid(z) -> A2[b] hi/lo
+        // ---- my logits -> log-likelihood terms, r = y - sigmoid(z) -> A2[b] hi/lo (chunk c-1's contraction 2 runs
+        // on the tensor pipe meanwhile: it is only waited for below, after the transcendental work)
         uint32_t hi[S::kZ], lo[S::kZ];
         const float* yy = sh.y[c % kRing] + S::kZ * slice;
         const float* vv = sh.valid[c % kRing] + S::kZ * slice;
@@ -351,6 +348,10 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const _
           hi[j] = tf32_round(r);
           lo[j] = tf32_round(r - __uint_as_float(hi[j]));
         }
+        // chunk c-1's contraction 2 is the last reader of A2[(c-1)%2] and the writer of D2; waiting for it before
+        // signal A also keeps every worker within one round of the issuer (the workers only ARRIVE on barriers 2 / 3)
+        if (c >= 1) take_g(c % S::kGroup == 0);
+        signal(2);
         tmem_st_n<S::kZ>(lane_addr + S::kColA2hi + S::R * b + S::kZ * slice, hi);
         tmem_st_n<S::kZ>(lane_addr + S::kColA2lo + S::R * b + S::kZ * slice, lo);
         signal(3);
