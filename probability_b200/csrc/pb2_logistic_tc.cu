@@ -63,6 +63,10 @@ __host__ __device__ inline int plane_offset(int NP, int n, int k) {
   return ((k >> 2) * (NP / 8) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 3) * 4;
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ uint32_t tf32_round(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 
 // N consecutive TMEM columns of my lane <-> registers, N split greedily into the x16 / x8 / x4 / x2 / x1 shapes
@@ -339,9 +343,11 @@ logistic_tc_kernel(const float* __restrict__ Theta, int B, int D, int N, const _
         for (int j = 0; j < S::kZ; ++j) {
           const float z = __uint_as_float(zq[j]);
           // softplus(z) = max(z, 0) + log1p(exp(-|z|)); sigmoid(z) from the same exponential
-          const float e = __expf(-fabsf(z));                 // same fast forms as the FP32 kernel (pb2_targets.cuh)
-          const float sp = fmaxf(z, 0.f) + __logf(1.0f + e);
-          const float inv = __fdividef(1.0f, 1.0f + e);
+          // the fast forms of the FP32 kernel (pb2_targets.cuh: __expf / __logf / __fdividef) without their
+          // denormal-range fix-ups: e below 2^-126 is flushed, where 1 + e == 1 anyway, and 1 + e is in [1, 2]
+          const float e = ex2_ftz(fabsf(z) * -1.4426950216293334961f);
+          const float sp = fmaxf(z, 0.f) + lg2_ftz(1.0f + e) * 0.693147182464599609375f;
+          const float inv = rcp_ftz(1.0f + e);
           const float sg = z >= 0.f ? inv : e * inv;
           ll += vv[j] * (yy[j] * z - sp);
           const float r = vv[j] * (yy[j] - sg);
