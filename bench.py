@@ -111,8 +111,31 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------
+def all_host_threads():
+  """BLAS threads = every host core for the CPU legs (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
+  try:
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=os.cpu_count())
+  except ImportError:
+    import contextlib
+    return contextlib.nullcontext()
+
+
+def blas_threads():
+  try:
+    from threadpoolctl import threadpool_info
+    return max([d.get('num_threads', 1) for d in threadpool_info()] or [1])
+  except ImportError:
+    return int(os.environ.get('OMP_NUM_THREADS', os.cpu_count()))
+
+
 def cpu_reference_arm(steps, warmup, budget_s=25.0):
   """The oracle port (lock-step batched NumPy restatement of nuts.py) on the host cores."""
+  with all_host_threads():
+    return _cpu_reference_arm(steps, warmup, budget_s)
+
+
+def _cpu_reference_arm(steps, warmup, budget_s):
   from oracle import mcmc as omcmc
   from oracle import rng as orng
   from oracle import targets as otargets
@@ -138,9 +161,10 @@ def cpu_reference_arm(steps, warmup, budget_s=25.0):
     n_grad += int(r['leapfrogs_taken'].sum())
     done += 1
   dt = time.perf_counter() - t0
-  return {'value': n_grad / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+  return {'value': n_grad / dt, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
           'sample': '%d chains x %d NUTS transitions (depth<=%d, eps=%.2f), NumPy float32 lock-step port of '
-                    'tfp nuts.py, BLAS threads = all cores; %.1fs' % (B, done, MAX_DEPTH, eps, dt)}, done, dt
+                    'tfp nuts.py, BLAS threads = %d of %d host cores; %.1fs' % (B, done, MAX_DEPTH, eps, blas_threads(),
+                                                                               os.cpu_count(), dt)}, done, dt
 
 
 def main():

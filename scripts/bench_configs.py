@@ -84,7 +84,17 @@ def gpu_run(name, state, kernel, steps, adapt, draws):
 
 
 def cpu_run(kind, otgt, x, eps, budget_s, **kw):
-  """oracle port on the host cores, bounded sample"""
+  """oracle port on the host cores (BLAS threads = all of them, also under torchrun's OMP_NUM_THREADS=1), bounded sample"""
+  try:
+    from threadpoolctl import threadpool_limits, threadpool_info
+  except ImportError:
+    return _cpu_run(kind, otgt, x, eps, budget_s, os.cpu_count(), **kw)
+  with threadpool_limits(limits=os.cpu_count()):
+    threads = max([d.get('num_threads', 1) for d in threadpool_info()] or [1])
+    return _cpu_run(kind, otgt, x, eps, budget_s, threads, **kw)
+
+
+def _cpu_run(kind, otgt, x, eps, budget_s, threads, **kw):
   lp, g = otgt.logp_grad(x)
   seed = orng.sanitize_seed(17, salt='mcmc.sample_chain')
   t0 = time.perf_counter()
@@ -100,7 +110,7 @@ def cpu_run(kind, otgt, x, eps, budget_s, **kw):
     x, lp, g = r['state'], r['target_log_prob'], r['grads']
     done += 1
   dt = time.perf_counter() - t0
-  return {'value': n_grad / dt, 'unit': 'grad-evals/s', 'cores': os.cpu_count(), 'kind': 'port',
+  return {'value': n_grad / dt, 'unit': 'grad-evals/s', 'cores': threads, 'kind': 'port',
           'sample': '%d chains x %d %s transitions, NumPy float32 port of the reference algorithm; %.1fs' % (
               x.shape[0], done, kind.upper(), dt)}
 
