@@ -6,7 +6,8 @@ sys.path.insert(0, '.')
 import probability_b200 as tfp
 from probability_b200 import _lib
 from oracle import targets as otargets
-dev = torch.device('cuda', 0)
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
 tg = tfp.targets.IllConditionedGaussian()
 rng = np.random.default_rng(0)
 L = np.linalg.cholesky(tg.covariance)
