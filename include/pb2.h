@@ -262,9 +262,12 @@ int pb2_da_init(pb2_ctx* ctx, float step_size, int num_adaptation_steps, float t
                 float exploration_shrinkage, float step_count_smoothing, float decay_rate,
                 float log_shrinkage_target /* NaN: log(10*step_size) */, int step, float error_sum,
                 float log_averaging_step, float* d_state /*[16]*/);
-/* (max, sum exp(la - max)) of la = min(0, finite_or(-inf)(log_accept_ratio)) over B chains */
+/* the 8-byte partial of B chains: the sum of their accept probabilities exp(min(0, finite_or(-inf)(log_accept_ratio)))
+ * as a little-endian 64-bit fixed-point integer in 2^-36 units (two 32-bit words in the float slots).  Integer sums are
+ * associative: partials of any split of the chains over launches or ranks combine to the same bits
+ * (reduce_logmeanexp over named axes, math/generic.py:221-274, distribute_lib.py:147-162). */
 int pb2_da_partial(pb2_ctx* ctx, const float* d_log_accept_ratio, int B, float* d_partial /*[2]*/);
-/* combine n_partials (max,sumexp) pairs, update the state and write the new step size */
+/* add n_partials partials, update the state with their mean over B_global chains and write the new step size */
 int pb2_da_apply(pb2_ctx* ctx, const float* d_partials /*[n,2]*/, int n_partials, long long B_global,
                  float* d_state, float* d_step_size_out /* nullable */);
 

@@ -515,7 +515,7 @@ int pb2_run(pb2_ctx* ctx, const pb2_target* tgt, const pb2_chain_layout* lay, co
       if (adapting) {
         if (int rc2 = launch_da_partial(ctx, p.lar_last, lay->B, ctx->d_partial)) return rc2;
         if (da_ranks) {
-          // every rank gathers all (max, sum-exp) pairs and combines them in rank order: the same bits everywhere
+          // every rank gathers all fixed-point partial sums and adds them: exact, the same bits everywhere
           if (int rc2 = comm_allgather(ctx, ctx->d_partial, ctx->d_partial + 2, 2)) return rc2;
           if (int rc2 = launch_da_apply(ctx, ctx->d_partial + 2, ctx->comm_size, lay->B_global, da->d_state, d_step_size, nullptr)) return rc2;
         } else if (int rc2 = launch_da_apply(ctx, ctx->d_partial, 1, lay->B, da->d_state, d_step_size, nullptr)) return rc2;

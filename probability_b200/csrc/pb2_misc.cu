@@ -123,53 +123,46 @@ int launch_rng_fill(pb2_ctx* ctx, Key key, Key key_hi, long long n, int layout, 
 // dual_averaging_step_size_adaptation.py:419-475; log_accept_prob getter
 // simple_step_size_adaptation.py:42-48; reduce_logmeanexp math/generic.py:221-274 via
 // distribute_lib.reduce_logsumexp :147-162.
+constexpr float kDaFixedPointScale = 68719476736.0f;   // 2^36
+
 __global__ void da_partial_kernel(const float* lar, int B, float* partial) {
-  __shared__ float sh[32];
-  float mx = -INFINITY;
+  // The partial is the SUM of the chains' accept probabilities exp(min(0, log_accept_ratio)) in 64-bit fixed point
+  // (2^-36 units; exact for p >= 2^-12, truncated below): integer addition is associative, so the statistic -- and with
+  // it the adapted step size -- is bit-identical however the chains are split over launches, blocks or ranks.
+  __shared__ unsigned long long sh[32];
+  unsigned long long s = 0ull;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     float v = lar[i];
     v = fminf(isfinite(v) ? v : -INFINITY, 0.f);
-    mx = fmaxf(mx, v);
+    s += (unsigned long long)(expf(v) * kDaFixedPointScale);
   }
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  mx = -INFINITY;
-  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) mx = fmaxf(mx, sh[k]);
-  __syncthreads();
-  const float ref = isfinite(mx) ? mx : 0.f;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    float v = lar[i];
-    v = fminf(isfinite(v) ? v : -INFINITY, 0.f);
-    s += expf(v - ref);
-  }
-  s = warp_sum(s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.f;
+    unsigned long long tot = 0ull;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += sh[k];
-    partial[0] = ref;
-    partial[1] = tot;
+    uint32_t* out = reinterpret_cast<uint32_t*>(partial);
+    out[0] = (uint32_t)tot;
+    out[1] = (uint32_t)(tot >> 32);
   }
 }
 
-__global__ void da_apply_kernel(const float* partials, int n, float B_global, float* st, float* step_out,
+__global__ void da_apply_kernel(const float* partials, int n, double B_global, float* st, float* step_out,
                                 float* step_seq_next) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float mx = -INFINITY;
-  for (int k = 0; k < n; ++k) mx = fmaxf(mx, partials[2 * k]);
-  float tot = 0.f;
-  for (int k = 0; k < n; ++k) tot += partials[2 * k + 1] * expf(partials[2 * k] - mx);
-  const float r = (mx + logf(tot)) - logf(B_global);  // log mean exp
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(partials);
+  unsigned long long tot = 0ull;
+  for (int k = 0; k < n; ++k) tot += (unsigned long long)w[2 * k] | ((unsigned long long)w[2 * k + 1] << 32);
+  // exp(log-mean-exp of the log accept probabilities) = their mean
+  const float mean_accept = (float)((double)tot / ((double)kDaFixedPointScale * B_global));
   float error_sum = st[0], log_avg = st[1];
   const float log_shrink = st[2];
   const int step_i = (int)st[3];
   const int n_adapt = (int)st[4];
   const float target = st[5], gamma = st[6], t0 = st[7], kappa = st[8];
   float step_size = st[9];
-  error_sum = error_sum + target - expf(r);
+  error_sum = error_sum + target - mean_accept;
   const float t = (float)step_i + 1.f;
   const float log_step = log_shrink - (error_sum * sqrtf(t)) / ((t0 + t) * gamma);
   const float eta = powf(t, -kappa);
@@ -194,7 +187,7 @@ int launch_da_partial(pb2_ctx* ctx, const float* d_lar, int B, float* d_partial)
 
 int launch_da_apply(pb2_ctx* ctx, const float* d_partials, int n, long long B_global, float* d_state,
                     float* d_step_out, float* d_step_seq_next) {
-  da_apply_kernel<<<1, 32, 0, ctx->stream>>>(d_partials, n, (float)B_global, d_state, d_step_out, d_step_seq_next);
+  da_apply_kernel<<<1, 32, 0, ctx->stream>>>(d_partials, n, (double)B_global, d_state, d_step_out, d_step_seq_next);
   ctx->launches += 1;
   return check_cuda(ctx, cudaGetLastError(), "da_apply_kernel");
 }

@@ -89,19 +89,16 @@ class SimpleStepSizeAdaptation(kernel_base.TransitionKernel):
     ctx.bind_stream()
     partial = torch.empty(2, dtype=torch.float32, device=lar.device)
     _lib.check(ctx.lib.pb2_da_partial(ctx.handle, _lib.ptr(lar), lar.numel(), _lib.ptr(partial)), ctx.handle)
+    # the partial is a 64-bit fixed-point sum (2^-36 units) of the accept probabilities: integer sums over the ranks
+    # are exact, so every sharding of the chains adapts with the same bits
+    total = partial.view(torch.int64).clone()
+    cnt = torch.tensor([lar.numel()], dtype=torch.int64, device=lar.device)
     dist = self._world()
-    cnt = torch.tensor(float(lar.numel()), device=lar.device)
-    mx, se = partial[0], partial[1]
     if dist is not None:
-      gmx = mx.clone()
-      dist.all_reduce(gmx, op=dist.ReduceOp.MAX)
-      safe = torch.where(torch.isfinite(gmx), gmx, torch.zeros_like(gmx))
-      se = se * torch.exp(torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx)) - safe)
-      se = torch.where(torch.isfinite(mx), se, torch.zeros_like(se))
-      dist.all_reduce(se)
+      dist.all_reduce(total)
       dist.all_reduce(cnt)
-      mx = gmx
-    return mx + torch.log(se) - torch.log(cnt)
+    mean = total.to(torch.float64) / (2.0 ** 36) / cnt.to(torch.float64)
+    return torch.log(mean).to(torch.float32).reshape(())
 
   def one_step(self, current_state, previous_kernel_results, seed=None):
     import torch

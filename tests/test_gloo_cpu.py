@@ -1,6 +1,6 @@
 """world_size-2 gloo test (CPU): the cross-rank pieces of the N>1 path that do not need a GPU --
-(i) combining per-rank (max, sum-exp) partials reproduces the unsharded reduce_logmeanexp that
-dual averaging uses (distribute_lib.py:147-162), (ii) chain shards driven by the same seed with
+(i) combining per-rank fixed-point partial sums of the accept probabilities reproduces the unsharded
+reduce_logmeanexp that dual averaging uses (distribute_lib.py:147-162), exactly for any split, (ii) chain shards driven by the same seed with
 global-chain-index counters reproduce the unsharded transition (oracle), (iii) row shards: the
 all-reduced packed (gradient | log-lik) equals the full-data value."""
 import os
@@ -33,14 +33,16 @@ def _worker(rank, world, port, q):
     lar[3] = np.nan
     mine = lar[rank * B:(rank + 1) * B]
     la = np.minimum(np.where(np.isfinite(mine), mine, -np.inf), 0).astype(np.float32)
-    mx = np.max(la); ref = mx if np.isfinite(mx) else np.float32(0)
-    part = torch.tensor([ref, np.sum(np.exp(la - ref), dtype=np.float32)])
-    gathered = [torch.zeros(2) for _ in range(world)]
+    # the partial: the accept probabilities summed as 64-bit fixed point in 2^-36 units (integer addition is
+    # associative: any split of the chains over ranks gives the same bits), gathered as raw bytes
+    fixed = lambda v: int(np.sum((np.exp(v).astype(np.float32) * np.float32(2.0 ** 36)).astype(np.uint64)))
+    part = torch.tensor([fixed(la)], dtype=torch.int64)
+    gathered = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(gathered, part)
-    g = torch.stack(gathered).numpy()
-    m = g[:, 0].max()
-    combined = m + np.log(np.sum(g[:, 1] * np.exp(g[:, 0] - m))) - np.log(Bg)
+    total = int(torch.stack(gathered).sum())
     la_all = np.minimum(np.where(np.isfinite(lar), lar, -np.inf), 0).astype(np.float32)
+    assert total == fixed(la_all)                       # sharded == unsharded, exactly
+    combined = np.log(total / 2.0 ** 36 / Bg)
     expect = omcmc.DualAveraging.reduce_logmeanexp(la_all)
     np.testing.assert_allclose(combined, expect, rtol=1e-6)
     # (ii) chain shards == unsharded (NUTS + HMC), then all ranks agree on the gathered result
