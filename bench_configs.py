@@ -91,6 +91,12 @@ def ess_block(tfp, draws, B, seconds, max_chains=1024):
 
 def cpu_port(kind, otgt, x, eps, budget_s, min_draws=4, **kw):
   """The oracle port on the host cores over a bounded sample; grad-evals/s and (cross-chain) min-ESS/s of its draws."""
+  import bench
+  with bench.all_host_threads():       # every host core, also under torchrun's OMP_NUM_THREADS=1
+    return _cpu_port(kind, otgt, x, eps, budget_s, min_draws, bench.blas_threads(), **kw)
+
+
+def _cpu_port(kind, otgt, x, eps, budget_s, min_draws, threads, **kw):
   from oracle import diagnostic as odiag
   from oracle import mcmc as omcmc
   from oracle import rng as orng
@@ -112,9 +118,10 @@ def cpu_port(kind, otgt, x, eps, budget_s, min_draws=4, **kw):
     if done >= kw.get('max_steps', 10 ** 9):
       break
   dt = time.perf_counter() - t0
-  out = {'value': n_grad / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+  out = {'value': n_grad / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
          'sample': '%d chains x %d %s transitions, NumPy float32 port of the reference algorithm '
-                   '(oracle/mcmc.py), BLAS threads = all cores; %.1fs' % (x.shape[0], done, kind.upper(), dt)}
+                   '(oracle/mcmc.py), BLAS threads = %d of %d host cores; %.1fs' % (x.shape[0], done, kind.upper(), threads,
+                                                                                    os.cpu_count(), dt)}
   if done >= 4 and x.shape[0] > 1:
     st = np.stack(draws)
     ess = odiag.effective_sample_size(st, cross_chain_dims=1, filter_beyond_positive_pairs=True, filter_threshold=None)
