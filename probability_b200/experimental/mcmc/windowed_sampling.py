@@ -65,9 +65,18 @@ def _windowed(kind, n_draws, target, n_chains, num_adaptation_steps, current_sta
   import torch
   seed = pb_random.sanitize_seed(seed, salt='windowed_adaptive_' + kind)
   D = target.dim
+  # chains sharded over ranks (experimental_chain_shard): step size and mass matrix are adapted on the statistics of ALL
+  # ranks' chains -- dual averaging reduces its accept statistic over the ranks, the running variance of every window is
+  # merged over the ranks in rank order -- like the reference's `experimental_chain_axis_names` (windowed_sampling.py)
+  shard = kernel_kwargs.get('experimental_chain_shard')
+  world = dassa.world_of('ranks' if shard is not None else None)
   if current_state is None:
-    # init_near_unconstrained_zero: Uniform(-2, 2) in the unconstrained space
-    u = pb_random.uniform((n_chains, D), seed=pb_random.fold_in(seed, 1000))
+    # init_near_unconstrained_zero: Uniform(-2, 2) in the unconstrained space (drawn for the global batch: a shard
+    # starts from its rows of it)
+    n_all = int(shard.num_chains_global) if shard is not None else n_chains
+    u = pb_random.uniform((n_all, D), seed=pb_random.fold_in(seed, 1000))
+    if shard is not None:
+      u = u[int(shard.chain_offset):int(shard.chain_offset) + n_chains]
     x = (4.0 * u - 2.0).contiguous()
     shapes, was_list = [(D,)], False
     state = x
@@ -80,6 +89,8 @@ def _windowed(kind, n_draws, target, n_chains, num_adaptation_steps, current_sta
   da_kw = dict(target_accept_prob=0.85)
   da_kw.update(dual_averaging_kwargs or {})
   da_kw.pop('num_adaptation_steps', None)
+  if world is not None:
+    da_kw.setdefault('experimental_reduce_chain_axis_names', 'ranks')
   first, slow, last = _get_window_sizes(int(num_adaptation_steps))
   md = preconditioning.DiagonalMomentum([torch.ones(s if len(s) else (), device=dev) for s in shapes])
 
@@ -109,6 +120,8 @@ def _windowed(kind, n_draws, target, n_chains, num_adaptation_steps, current_sta
       rv = RunningVariance.from_shape(shapes, dev, was_list)
       tail = [s[length - n_var:] for s in st] if was_list else st[length - n_var:]
       rv = rv.update(tail)
+      if world is not None:
+        rv = rv.merged_over_ranks(world)
       md = preconditioning.DiagonalMomentum(rv.variance() if was_list else [rv.variance()])
     if not discard_tuning:
       tune_states.append(st)

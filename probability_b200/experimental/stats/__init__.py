@@ -7,6 +7,27 @@ from probability_b200 import _lib
 from probability_b200.mcmc import _engine
 
 
+def merge_moment_states(states):
+  """Chan's merge, in list order, of `[count, mean[D], sum of squared deviations[D]]` states (float64 inside): the
+  moments of the union of the observations.  With the ranks' states gathered in rank order every rank gets the same
+  bits (the pooled estimate windowed adaptation uses when the chains are sharded, windowed_sampling.py:322-347 with
+  `experimental_chain_axis_names`)."""
+  import torch
+  D = (states[0].numel() - 1) // 2
+  first = states[0].double()
+  n, mean, m2 = first[0], first[1:1 + D], first[1 + D:]
+  for s in states[1:]:
+    s = s.double()
+    nb, mb, m2b = s[0], s[1:1 + D], s[1 + D:]
+    tot = n + nb
+    safe = torch.clamp(tot, min=1.0)
+    delta = mb - mean
+    mean = mean + delta * (nb / safe)
+    m2 = m2 + m2b + delta * delta * (n * nb / safe)
+    n = tot
+  return torch.cat([n.reshape(1), mean, m2]).float().contiguous()
+
+
 class RunningVariance(object):
   """`update(new_sample)` folds a batch of observations into the running moments; every row of the flattened
   `[n, D]` batch is one observation (the reference's `update(x, axis=0)`).  Immutable like the reference's: `update`
@@ -69,6 +90,13 @@ class RunningVariance(object):
     _lib.check(ctx.lib.pb2_running_moments_update(ctx.handle, _lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(st)),
                ctx.handle)
     return RunningVariance(st, self.shapes, self.was_list)
+
+  def merged_over_ranks(self, dist, group=None):
+    """The moments of all ranks' observations (every rank gets the same object state)."""
+    import torch
+    gathered = [torch.empty_like(self.state) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(gathered, self.state.contiguous(), group=group)
+    return RunningVariance(merge_moment_states(gathered), self.shapes, self.was_list)
 
   @property
   def num_samples(self):

@@ -103,6 +103,28 @@ def check(rank, world, dev, mode):
     dist.all_gather(s, sh.all_states.contiguous())
     for a in s:
       assert torch.equal(a, sh.all_states)
+  # ---------------- (c) windowed adaptation with sharded chains: step size and mass matrix are adapted on ALL ranks'
+  # chains (cross-rank accept statistic + rank-ordered merge of the running moments), so every rank ends with the same
+  # step size and the same variance estimate, and those agree statistically with the unsharded run of the same batch
+  tgw = tfp.targets.EightSchools()
+  Bw = 64
+  xw = (np.array([0, 0] + [1] * 8) + 0.3 * np.random.default_rng(5).standard_normal((Bw * world, 10))).astype(np.float32)
+  import probability_b200.experimental.mcmc as emcmc
+  dw, tw = emcmc.windowed_adaptive_nuts(20, tgw, n_chains=Bw, num_adaptation_steps=120, max_tree_depth=6,
+                                        current_state=torch.tensor(xw[rank * Bw:(rank + 1) * Bw], device=dev),
+                                        experimental_chain_shard=tfp.mcmc.ChainShard(rank * Bw, Bw * world), seed=9)
+  flatv = lambda t: torch.cat([v.reshape(-1) for v in (t['variance_scaling'] if isinstance(t['variance_scaling'], (list, tuple))
+                                                       else [t['variance_scaling']])])
+  mine = torch.cat([tw['step_size'][:1].reshape(-1), flatv(tw)]).contiguous()
+  gw = [torch.zeros_like(mine) for _ in range(world)]
+  dist.all_gather(gw, mine)
+  for a in gw:
+    assert torch.equal(a, mine), 'ranks adapted to different step sizes / mass matrices'
+  df, tf_ = emcmc.windowed_adaptive_nuts(20, tgw, n_chains=Bw * world, num_adaptation_steps=120, max_tree_depth=6,
+                                         current_state=torch.tensor(xw, device=dev), seed=9)
+  vs, vf = flatv(tw).cpu().numpy(), flatv(tf_).cpu().numpy()
+  np.testing.assert_allclose(vs, vf, rtol=0.35)
+  np.testing.assert_allclose(float(tw['step_size'][0]), float(tf_['step_size'][0]), rtol=0.35)
   dist.barrier()
   if rank == 0:
     print('multi-GPU invariants hold with %s' % mode, flush=True)

@@ -78,3 +78,24 @@ def test_state_part_shard_axes_are_size_one_only(dist_mod):
   dist_mod.register_axis('model', 0, 4)
   with pytest.raises(NotImplementedError):
     _engine.check_shard_axis_names([['model'], None])
+
+
+def test_merged_running_moments_equal_the_pooled_moments():
+  """experimental.stats.merge_moment_states: Chan's merge of per-rank [count, mean, M2] states == the moments of the
+  pooled observations (what windowed adaptation uses when the chains are sharded over ranks)."""
+  import torch
+  from probability_b200.experimental.stats import merge_moment_states
+  rng = np.random.default_rng(3)
+  D = 7
+  chunks = [rng.standard_normal((n, D)) * np.arange(1, D + 1) + 3.0 for n in (5, 1, 40, 17)]
+  states = []
+  for c in chunks:
+    m = c.mean(0)
+    states.append(torch.tensor(np.concatenate([[len(c)], m, ((c - m) ** 2).sum(0)]), dtype=torch.float32))
+  states.insert(2, torch.zeros(1 + 2 * D))              # a rank without observations
+  got = merge_moment_states(states).numpy()
+  pooled = np.concatenate(chunks)
+  assert got[0] == len(pooled)
+  np.testing.assert_allclose(got[1:1 + D], pooled.mean(0), rtol=1e-5)
+  np.testing.assert_allclose(got[1 + D:] / got[0], pooled.var(0), rtol=1e-5)
+  np.testing.assert_array_equal(merge_moment_states([states[0]]).numpy(), states[0].numpy())
