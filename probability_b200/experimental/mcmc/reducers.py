@@ -14,6 +14,7 @@ import numpy as np
 from probability_b200 import _lib
 from probability_b200 import random as pb_random
 from probability_b200.mcmc import _engine
+from probability_b200.mcmc import kernel as kernel_lib
 from probability_b200.mcmc import sample as sample_lib
 
 
@@ -24,9 +25,31 @@ class _ChainMoments(object):
     import torch
     self.B, self.D = B, D
     self.state = torch.zeros(1 + 2 * B * D, dtype=torch.float32, device=device)
+    self.comoment = None
+
+  def _update_comoment(self, states):
+    """Chan's merge of the chunk's centred Gram matrices (one batched library GEMM per chunk) into the running
+    co-moment, using the running count / mean BEFORE this chunk (sample_stats.py RunningCovariance.update)."""
+    import torch
+    n = float(states.shape[0])
+    na = self.count.clone()
+    mb = states.mean(0)                                         # [B, D]
+    xc = (states - mb).permute(1, 2, 0).contiguous()            # [B, D, n]
+    gram = torch.bmm(xc, xc.transpose(1, 2))                    # [B, D, D]
+    delta = mb - self.mean
+    w = na * n / (na + n)
+    self.comoment += gram + w * delta[:, :, None] * delta[:, None, :]
+
+  def track_comoment(self):
+    """Also keep the per-chain co-moment matrix sum_t (x_t - mean)(x_t - mean)^T [B, D, D] (CovarianceReducer)."""
+    import torch
+    if self.comoment is None:
+      self.comoment = torch.zeros(self.B, self.D, self.D, dtype=torch.float32, device=self.state.device)
 
   def update(self, states):
     """states: [n, B, D] float32 CUDA."""
+    if self.comoment is not None:
+      self._update_comoment(states)
     x = states.reshape(states.shape[0], self.B * self.D).contiguous()
     ctx = _lib.Context.get(x.device)
     ctx.bind_stream()
@@ -87,6 +110,42 @@ class VarianceReducer(Reducer):
     return self._unflat(st, st.m2 / (st.count - float(self.ddof)))
 
 
+class CovarianceReducer(Reducer):
+  """covariance_reducer.py:43-220: running covariance of the state over the steps, per chain.  `event_ndims` = 1 (every
+  state part `[chains, d]`: result `[chains, d, d]` per part) or 0 (variances, the VarianceReducer).  The reference's
+  default `event_ndims=None` treats the chain axis as part of the event (a `[chains, d, chains, d]` matrix) and is not
+  offered; nor are `transform_fn`s (the reducers see states only)."""
+  needs_comoment = True
+
+  def __init__(self, event_ndims=1, ddof=0, name=None):
+    del name
+    if event_ndims not in (0, 1):
+      raise NotImplementedError('CovarianceReducer: event_ndims must be 0 or 1 (covariance within a chain)')
+    self.event_ndims, self.ddof = event_ndims, ddof
+    self.needs_comoment = event_ndims == 1
+
+  def initialize(self, initial_chain_state, initial_kernel_results=None):
+    st = super(CovarianceReducer, self).initialize(initial_chain_state, initial_kernel_results)
+    if self.event_ndims == 1:
+      if any(len(sh) != 1 for sh in st.shapes):
+        raise ValueError('CovarianceReducer(event_ndims=1) needs state parts of shape [chains, d]')
+      st.track_comoment()
+    return st
+
+  def finalize(self, st):
+    denom = st.count - float(self.ddof)
+    if self.event_ndims == 0:
+      return self._unflat(st, st.m2 / denom)
+    if st.comoment is None:
+      raise ValueError('the reducer state does not carry co-moments (initialize it with this reducer)')
+    cov = st.comoment / denom
+    outs, off = [], 0
+    for n in _engine.part_sizes_of(st.shapes):
+      outs.append(cov[:, off:off + n, off:off + n])
+      off += n
+    return outs if st.was_list else outs[0]
+
+
 class PotentialScaleReductionReducer(Reducer):
   """potential_scale_reduction_reducer.py:36-160: R-hat from per-chain running means and variances
   (diagnostic.py:476-567 with independent_chain_ndims = 1)."""
@@ -142,6 +201,10 @@ def sample_fold(num_steps, current_state, previous_kernel_results=None, kernel=N
   if shared is None:
     shared = _ChainMoments(B, D, x.device)
     shared.shapes, shared.was_list = shapes, was_list
+    if any(getattr(r, 'needs_comoment', False) for r in reducers if r is not None):
+      if any(len(sh) != 1 for sh in shapes):
+        raise ValueError('CovarianceReducer(event_ndims=1) needs state parts of shape [chains, d]')
+      shared.track_comoment()
   chunk = int(max(1, min(int(num_steps), experimental_chunk_bytes // max(1, 4 * B * D))))
   state, pkr = current_state, previous_kernel_results
   done = 0
@@ -164,3 +227,64 @@ def sample_fold(num_steps, current_state, previous_kernel_results=None, kernel=N
   if return_final_reducer_states:
     out = (out, shared)
   return SampleFoldResults(out, state, pkr)
+
+
+WithReductionsKernelResults = collections.namedtuple('WithReductionsKernelResults',
+                                                     ['reduction_results', 'inner_results'])
+
+
+def _map_reducers(fn, reducer, *rest):
+  if isinstance(reducer, (list, tuple)):
+    return type(reducer)(fn(*args) for args in zip(reducer, *rest))
+  return fn(reducer, *rest)
+
+
+class WithReductions(kernel_lib.TransitionKernel):
+  """with_reductions.py:41-180: a TransitionKernel that steps `inner_kernel` and folds every new state into `reducer`
+  (a Reducer or a list / tuple of them); the reducer states ride in `kernel_results.reduction_results`, finalize them
+  with `reducer.finalize(state)`.  The per-step protocol: one transition + one moments update per `one_step` (use
+  `sample_fold` for the chunked, fused form).  Reducer states are updated in place (device buffers), so results of an
+  earlier step alias the current ones."""
+
+  def __init__(self, inner_kernel, reducer, adjust_kr_fn=lambda kr: kr, name=None):
+    self._parameters = dict(inner_kernel=inner_kernel, reducer=reducer, adjust_kr_fn=adjust_kr_fn, name=name)
+
+  inner_kernel = property(lambda self: self._parameters['inner_kernel'])
+  reducer = property(lambda self: self._parameters['reducer'])
+  adjust_kr_fn = property(lambda self: self._parameters['adjust_kr_fn'])
+  name = property(lambda self: self._parameters['name'])
+  parameters = property(lambda self: self._parameters)
+  is_calibrated = property(lambda self: self.inner_kernel.is_calibrated)
+
+  def bootstrap_results(self, init_state, inner_results=None, previous_reducer_state=None):
+    """The initial state does not count as a sample: the reducer states start as empty streams."""
+    if inner_results is None:
+      inner_results = self.inner_kernel.bootstrap_results(init_state)
+    if previous_reducer_state is None:
+      previous_reducer_state = _map_reducers(lambda r: r.initialize(init_state, inner_results), self.reducer)
+    return WithReductionsKernelResults(previous_reducer_state, inner_results)
+
+  def one_step(self, current_state, previous_kernel_results, seed=None):
+    new_state, inner_results = self.inner_kernel.one_step(current_state, previous_kernel_results.inner_results,
+                                                          seed=seed)
+    adj = self.adjust_kr_fn(inner_results)
+    red = _map_reducers(lambda r, st: r.one_step(new_state, st, previous_kernel_results=adj), self.reducer,
+                        previous_kernel_results.reduction_results)
+    return new_state, WithReductionsKernelResults(red, inner_results)
+
+
+def step_kernel(num_steps, current_state, previous_kernel_results=None, kernel=None,
+                return_final_kernel_results=False, parallel_iterations=10, seed=None, name=None):
+  """step.py:29-106: `num_steps` transitions of `kernel` from `current_state`, nothing traced; returns the end state
+  (and the final kernel results).  Seeds follow the reference's loop: `step_seed, seed = split_seed(seed)` per step."""
+  del parallel_iterations, name
+  if kernel is None:
+    raise ValueError('`kernel` is required')
+  seed = pb_random.sanitize_seed(seed, salt='mcmc_step_kernel')
+  if previous_kernel_results is None:
+    previous_kernel_results = kernel.bootstrap_results(current_state)
+  state, kr = current_state, previous_kernel_results
+  for _ in range(int(num_steps)):
+    step_seed, seed = pb_random.split_seed(seed)
+    state, kr = kernel.one_step(state, kr, seed=step_seed)
+  return (state, kr) if return_final_kernel_results else state

@@ -278,3 +278,56 @@ def test_sample_fold_streaming_reducers(tfp):
   np.testing.assert_allclose(got_rhat, ref_rhat, rtol=2e-3)
   for a, b in zip(out.end_state, st):
     np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+
+
+def test_covariance_reducer_with_reductions_and_step_kernel(tfp):
+  """covariance_reducer.py / with_reductions.py:41 / step.py:29: (i) the per-chain running covariance of a chunked
+  `sample_fold` run equals np.cov of the materialised history; (ii) a `WithReductions` kernel driven by `step_kernel`
+  (one transition + one fold per step) ends in the same state as the step loop and its reducers hold the statistics of
+  exactly the states it visited; (iii) `step_kernel` follows the reference's seed loop."""
+  exp = tfp.experimental.mcmc
+  tg = tfp.targets.IllConditionedGaussian()
+  rng = np.random.default_rng(4)
+  x0 = t((rng.standard_normal((24, 100)) @ np.linalg.cholesky(tg.covariance).T).astype(np.float32))
+  k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.5, num_leapfrog_steps=4)
+  n_steps = 33
+  chunk_bytes = 8 * 24 * 100 * 4
+  out = exp.sample_fold(n_steps, x0, kernel=k, reducer=[exp.CovarianceReducer(ddof=1), exp.VarianceReducer(ddof=1)],
+                        seed=3, experimental_chunk_bytes=chunk_bytes)
+  cov, var = out.reduction_results
+  seed = tfp.random.sanitize_seed(3, salt='mcmc.sample_fold')
+  st, pkr, hist, done = x0, k.bootstrap_results(x0), [], 0
+  while done < n_steps:
+    n = min(8, n_steps - done)
+    cs, seed = tfp.random.split_seed(seed)
+    r = tfp.mcmc.sample_chain(n, st, previous_kernel_results=pkr, kernel=k, trace_fn=None, seed=cs,
+                              return_final_kernel_results=True)
+    hist.append(r.all_states.cpu().numpy())
+    st, pkr, done = r.all_states[-1], r.final_kernel_results, done + n
+  h = np.concatenate(hist).astype(np.float64)                  # [n_steps, B, D]
+  assert tuple(cov.shape) == (24, 100, 100)
+  for b in (0, 7, 23):
+    ref = np.cov(h[:, b, :], rowvar=False, ddof=1)
+    np.testing.assert_allclose(cov[b].cpu().numpy(), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+  np.testing.assert_allclose(torch.diagonal(cov, dim1=1, dim2=2).cpu().numpy(), var.cpu().numpy(), rtol=1e-3, atol=1e-5)
+  with pytest.raises(NotImplementedError):
+    exp.CovarianceReducer(event_ndims=None)
+  # (ii) WithReductions + step_kernel == the step loop with the same seeds
+  reds = [exp.ExpectationsReducer(), exp.CovarianceReducer()]
+  wk = exp.WithReductions(k, reds)
+  assert wk.is_calibrated and wk.inner_kernel is k
+  end, kr = exp.step_kernel(9, x0, kernel=wk, return_final_kernel_results=True, seed=11)
+  seed = tfp.random.sanitize_seed(11, salt='mcmc_step_kernel')
+  st, pkr, visited = x0, k.bootstrap_results(x0), []
+  for _ in range(9):
+    ss, seed = tfp.random.split_seed(seed)
+    st, pkr = k.one_step(st, pkr, seed=ss)
+    visited.append(st.cpu().numpy())
+  np.testing.assert_array_equal(end.cpu().numpy(), st.cpu().numpy())
+  v = np.stack(visited).astype(np.float64)
+  mean_w, cov_w = [r.finalize(s) for r, s in zip(reds, kr.reduction_results)]
+  np.testing.assert_allclose(mean_w.cpu().numpy(), v.mean(0), rtol=1e-4, atol=1e-4)
+  ref = np.cov(v[:, 5, :], rowvar=False, ddof=0)
+  np.testing.assert_allclose(cov_w[5].cpu().numpy(), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+  # the bare driver returns only the state
+  np.testing.assert_array_equal(exp.step_kernel(9, x0, kernel=k, seed=11).cpu().numpy(), st.cpu().numpy())
