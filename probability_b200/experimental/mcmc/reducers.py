@@ -288,3 +288,36 @@ def step_kernel(num_steps, current_state, previous_kernel_results=None, kernel=N
     step_seed, seed = pb_random.split_seed(seed)
     state, kr = kernel.one_step(state, kr, seed=step_seed)
   return (state, kr) if return_final_kernel_results else state
+
+
+SampleDiscardingKernelResults = collections.namedtuple('SampleDiscardingKernelResults',
+                                                       ['call_counter', 'inner_results'])
+
+
+class SampleDiscardingKernel(kernel_lib.TransitionKernel):
+  """sample_discarding_kernel.py:40-175: burn-in and thinning as a kernel -- the first `one_step` advances the inner
+  kernel `num_burnin_steps + num_steps_between_results + 1` times, every later one `num_steps_between_results + 1`
+  times (through `step_kernel`, seeded with this step's seed), so a `WithReductions` wrapped around it only sees the
+  states that survive."""
+
+  def __init__(self, inner_kernel, num_burnin_steps=0, num_steps_between_results=0, name=None):
+    self._parameters = dict(inner_kernel=inner_kernel, num_burnin_steps=num_burnin_steps,
+                            num_steps_between_results=num_steps_between_results, name=name)
+
+  inner_kernel = property(lambda self: self._parameters['inner_kernel'])
+  num_burnin_steps = property(lambda self: self._parameters['num_burnin_steps'])
+  num_steps_between_results = property(lambda self: self._parameters['num_steps_between_results'])
+  name = property(lambda self: self._parameters['name'])
+  is_calibrated = property(lambda self: self.inner_kernel.is_calibrated)
+
+  def bootstrap_results(self, init_state, inner_results=None):
+    if inner_results is None:
+      inner_results = self.inner_kernel.bootstrap_results(init_state)
+    return SampleDiscardingKernelResults(0, inner_results)
+
+  def one_step(self, current_state, previous_kernel_results, seed=None):
+    calls = int(previous_kernel_results.call_counter)
+    skip = int(self.num_steps_between_results) + (int(self.num_burnin_steps) if calls == 0 else 0)
+    state, inner = step_kernel(skip + 1, current_state, previous_kernel_results=previous_kernel_results.inner_results,
+                               kernel=self.inner_kernel, return_final_kernel_results=True, seed=seed)
+    return state, SampleDiscardingKernelResults(calls + 1, inner)

@@ -331,3 +331,28 @@ def test_covariance_reducer_with_reductions_and_step_kernel(tfp):
   np.testing.assert_allclose(cov_w[5].cpu().numpy(), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
   # the bare driver returns only the state
   np.testing.assert_array_equal(exp.step_kernel(9, x0, kernel=k, seed=11).cpu().numpy(), st.cpu().numpy())
+
+
+def test_sample_discarding_kernel_is_burnin_and_thinning(tfp):
+  """sample_discarding_kernel.py:40-175: the first step takes burn-in + thinning + 1 inner transitions, later steps
+  thinning + 1; wrapped in WithReductions the reducers see the surviving states only."""
+  exp = tfp.experimental.mcmc
+  tg = tfp.targets.EightSchools()
+  x0 = t((np.array([0, 0] + [1] * 8) + 0.2 * np.random.default_rng(1).standard_normal((32, 10))).astype(np.float32))
+  k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=0.3, num_leapfrog_steps=3)
+  dk = exp.SampleDiscardingKernel(k, num_burnin_steps=4, num_steps_between_results=2)
+  kr = dk.bootstrap_results(x0)
+  assert kr.call_counter == 0 and dk.is_calibrated
+  s1, kr1 = dk.one_step(x0, kr, seed=(5, 6))
+  s2, kr2 = dk.one_step(s1, kr1, seed=(7, 8))
+  assert kr2.call_counter == 2
+  # the same transitions by hand: 4 + 2 + 1 steps seeded from (5, 6), then 2 + 1 from (7, 8)
+  a = exp.step_kernel(7, x0, kernel=k, seed=(5, 6))
+  np.testing.assert_array_equal(s1.cpu().numpy(), a.cpu().numpy())
+  b = exp.step_kernel(3, a, kernel=k, seed=(7, 8))     # kernel results after a bootstrap at `a` equal the carried ones
+  np.testing.assert_array_equal(s2.cpu().numpy(), b.cpu().numpy())
+  # the onion: reducers over the surviving states
+  wk = exp.WithReductions(dk, exp.ExpectationsReducer())
+  end, wkr = exp.step_kernel(5, x0, kernel=wk, return_final_kernel_results=True, seed=3)
+  assert wkr.inner_results.call_counter == 5
+  assert float(wkr.reduction_results.count) == 5.0
