@@ -25,10 +25,15 @@ tensorflow_probability/python/):
 PINNING STATUS
   * NUTS instruction tables, dual-averaging constants, R-hat, _reduce_variance:
     pinned by the reference's own known-answer tests (tests/test_oracle_pins.py).
-  * RNG bit stream: pinned against the Random123 Threefry-2x32-20 KATs and the
-    JAX-documented values for split/normal; the reference holds NO bit-level
-    golden vectors for the JAX substrate, and neither jax nor tensorflow is
-    installable here, so against a *live* reference: "parity unpinned".
+  * RNG bit stream: pinned against the Random123 Threefry-2x32-20 KATs and on
+    the outputs of a LIVE JAX run that the reference itself keeps -- the executed
+    cells of examples/jupyter_notebooks/TensorFlow_Probability_on_JAX.ipynb
+    (PRNGKey(0), random.split, random.normal on the key and on both children,
+    tfd.Normal(0, 1).sample(seed=key); tests/golden/jax_notebook_rng.json, made
+    by tests/golden/make_golden.py).  That covers the block function, the
+    original key-split layout and the bits -> uniform -> normal transform; the
+    partitionable layout has no reference-held vector (JAX-documented values
+    only), and neither jax nor tensorflow is installable here.
   * HMC/NUTS transitions: the reference cannot be executed in this image
     (needs tensorflow or jax); pinned only through the reference's
     statistical/invariant tests restated in tests/.  "parity unpinned" for

@@ -8,6 +8,12 @@ S&P 500 series are plain NumPy/Python files, importable without tensorflow/jax:
                                        .../targets/ground_truth/stochastic_volatility_sp500.py
   nuts_tables_depth4.json           <- the literal pins of tensorflow_probability/python/mcmc/nuts_test.py:191-215
   dual_averaging_pins.json          <- tensorflow_probability/python/mcmc/dual_averaging_step_size_adaptation_test.py:51-57
+  jax_notebook_rng.json             <- the executed cells of tensorflow_probability/examples/jupyter_notebooks/
+                                       TensorFlow_Probability_on_JAX.ipynb: outputs of a LIVE JAX run that the
+                                       reference keeps (PRNGKey(0), random.split, random.normal on the key and on
+                                       both split keys, tfd.Normal(0, 1).sample(seed=PRNGKey(0)), and a jitted
+                                       split -> normal -> exp chain) -- the reference-held pin of the threefry stream,
+                                       the key split and the uniform -> normal transform of the seed contract (R1)
 """
 import importlib.util
 import json
@@ -53,6 +59,38 @@ def main():
   pins['_INITIAL_T'] = float(re.search(r'^_INITIAL_T = ([0-9.]+)', src, re.M).group(1))
   pins['_EXPLORATION_SHRINKAGE'] = float(re.search(r'^_EXPLORATION_SHRINKAGE = ([0-9.]+)', src, re.M).group(1))
   json.dump(pins, open(os.path.join(HERE, 'dual_averaging_pins.json'), 'w'), indent=1)
+  # ---- JAX outputs held by the reference's own notebook (cell source -> printed output)
+  nb_path = 'tensorflow_probability/examples/jupyter_notebooks/TensorFlow_Probability_on_JAX.ipynb'
+  nb = json.load(open(os.path.join(REF, nb_path)))
+
+  def output_of(fragment):
+    for i, c in enumerate(nb['cells']):
+      if c['cell_type'] == 'code' and fragment in ''.join(c['source']):
+        outs = []
+        for o in c.get('outputs', []):
+          if 'text' in o:
+            outs.append(''.join(o['text']))
+          elif 'text/plain' in o.get('data', {}):
+            outs.append(''.join(o['data']['text/plain']))
+        return i, ' '.join(outs)
+    raise KeyError(fragment)
+
+  num = r'-?\d+\.?\d*(?:e-?\d+)?'
+  fl = lambda txt: [float(v) for v in re.findall(num, txt)]
+  rng = {'source': nb_path, 'cells': {}}
+  for name, frag, parse in [
+      ('prng_key_0', 'key = random.PRNGKey(0)  # Creates a key', lambda t: [int(v) for v in re.findall(r'\d+', t)]),
+      ('normal_key_0', 'print(random.normal(key))', lambda t: fl(t)[0]),
+      ('split_key_0', 'key1, key2 = random.split(key, num=2)',
+       lambda t: np.asarray([int(v) for v in re.findall(r'\d+', t)]).reshape(2, 2).tolist()),
+      ('normal_split_keys', 'print(random.normal(key1), random.normal(key2))', lambda t: fl(t)[:2]),
+      ('tfd_normal_sample_key_0', 'tfd.Normal(0., 1.).sample(seed=random.PRNGKey(0))',
+       lambda t: fl(t.replace('float32', ''))[0]),
+      ('split_normal_exp_mean_variance', 'def random_distribution(key):', lambda t: fl(t)[:2])]:
+    cell, txt = output_of(frag)
+    rng[name] = parse(txt)
+    rng['cells'][name] = cell
+  json.dump(rng, open(os.path.join(HERE, 'jax_notebook_rng.json'), 'w'), indent=1)
   print('golden fixtures written to', HERE)
 
 

@@ -64,6 +64,16 @@ def test_rng_known_answers(tfp):
                                 [[4146024105, 967050713], [2718843009, 1272950319]])
   np.testing.assert_array_equal(tfp.random.split_seed(orng.key(0), layout=0),
                                 [[1797259609, 2579123966], [928981903, 3453687069]])
+  # the JAX outputs the reference's executed notebook holds (tests/golden/jax_notebook_rng.json, make_golden.py):
+  # the CUDA generator reproduces split / normal on the key and on both children
+  import json
+  import os
+  g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'jax_notebook_rng.json')))
+  kids = tfp.random.split_seed(orng.key(0), layout=1)
+  np.testing.assert_array_equal(kids, g['split_key_0'])
+  draw = lambda kk: float(tfp.random.normal((1,), seed=kk, device=dev(), layout=1).cpu().numpy()[0])
+  np.testing.assert_allclose(draw(orng.key(0)), g['normal_key_0'], rtol=2e-7)
+  np.testing.assert_allclose([draw(kids[0]), draw(kids[1])], g['normal_split_keys'], rtol=2e-7)
 
 
 def test_rng_2d_shape_row_major(tfp):

@@ -9,7 +9,7 @@ from oracle import rng as orng
 from oracle import targets as otargets
 
 
-# ---- RNG: Random123 KATs + jax-documented values -------------------------------------
+# ---- RNG: Random123 KATs, jax-documented values, and the JAX outputs held by the reference's notebook -------------------------------------
 def test_threefry_random123_kats():
   cases = [((0, 0), (0, 0), (0x6b200159, 0x99ba4efe)),
            ((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x1cb996fc, 0xbb002be7)),
@@ -25,6 +25,27 @@ def test_jax_documented_values():
   np.testing.assert_array_equal(orng.split(orng.key(0), 2, orng.PARTITIONABLE),
                                 [[1797259609, 2579123966], [928981903, 3453687069]])
   np.testing.assert_allclose(orng.normal(orng.key(0), (1,), orng.ORIGINAL), [-0.20584227], rtol=1e-6)
+
+
+def test_rng_reproduces_the_jax_outputs_the_reference_keeps():
+  """tests/golden/jax_notebook_rng.json: outputs of a live JAX run held by the reference's own executed notebook
+  (examples/jupyter_notebooks/TensorFlow_Probability_on_JAX.ipynb cells 35, 49, 96-102; extracted by make_golden.py).
+  They pin the threefry stream, the key split and the bits -> uniform -> normal transform of the seed contract on
+  reference-held vectors: PRNGKey(0), split, normal on the key and on both children, and tfd.Normal.sample(seed=key)
+  == jax.random.normal(key) (the JAX substrate's samplers.normal adds no salt, internal/samplers.py:308-325)."""
+  import json, os
+  g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'jax_notebook_rng.json')))
+  k = orng.key(0)
+  np.testing.assert_array_equal(k, g['prng_key_0'])
+  np.testing.assert_allclose(orng.normal(k, (1,), orng.ORIGINAL)[0], g['normal_key_0'], rtol=2e-7)
+  np.testing.assert_allclose(orng.normal(k, (1,), orng.ORIGINAL)[0], g['tfd_normal_sample_key_0'], rtol=2e-7)
+  kids = orng.split(k, 2, orng.ORIGINAL)
+  np.testing.assert_array_equal(kids, g['split_key_0'])
+  z = [orng.normal(kk, (1,), orng.ORIGINAL)[0] for kk in kids]
+  np.testing.assert_allclose(z, g['normal_split_keys'], rtol=2e-7)
+  loc, var = g['split_normal_exp_mean_variance']        # Normal(normal(k1), exp(normal(k2))): mean, variance
+  np.testing.assert_allclose(z[0], loc, rtol=2e-7)
+  np.testing.assert_allclose(np.exp(np.float32(z[1])) ** 2, var, rtol=1e-6)
 
 
 def test_sample_chain_salt():
