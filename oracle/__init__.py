@@ -29,8 +29,9 @@ PINNING STATUS
     the outputs of a LIVE JAX run that the reference itself keeps -- the executed
     cells of examples/jupyter_notebooks/TensorFlow_Probability_on_JAX.ipynb
     (PRNGKey(0), random.split, random.normal on the key and on both children,
-    tfd.Normal(0, 1).sample(seed=key); tests/golden/jax_notebook_rng.json, made
-    by tests/golden/make_golden.py).  That covers the block function, the
+    tfd.Normal(0, 1).sample(seed=key); plus multi-element and 2-d draws from
+    discussion/examples/TFP_and_Jax.ipynb and Distributed_Inference_with_JAX.ipynb;
+    tests/golden/jax_notebook_rng.json, made by tests/golden/make_golden.py).  That covers the block function, the
     original key-split layout and the bits -> uniform -> normal transform; the
     partitionable layout has no reference-held vector (JAX-documented values
     only), and neither jax nor tensorflow is installable here.

@@ -90,6 +90,34 @@ def main():
     cell, txt = output_of(frag)
     rng[name] = parse(txt)
     rng['cells'][name] = cell
+  # two more executed notebooks: multi-element draws (the counter layout of a stream) and a 2-d shape
+  def notebook_output(nb_rel, fragment):
+    nb2 = json.load(open(os.path.join(REF, nb_rel)))
+    for i, c in enumerate(nb2['cells']):
+      if c['cell_type'] == 'code' and fragment in ''.join(c['source']):
+        outs = []
+        for o in c.get('outputs', []):
+          if 'text' in o:
+            outs.append(''.join(o['text']))
+          elif 'text/plain' in o.get('data', {}):
+            outs.append(''.join(o['data']['text/plain']))
+        return i, ' '.join(outs)
+    raise KeyError(fragment)
+
+  more = {}
+  nb_a = 'discussion/examples/TFP_and_Jax.ipynb'
+  cell, txt = notebook_output(nb_a, 'tf.random.stateless_uniform([1, 2], seed=random.PRNGKey(0))')
+  more['uniform_1x2_key_0'] = {'source': nb_a, 'cell': cell, 'value': fl(txt.replace('float32', ''))[:2]}
+  cell, txt = notebook_output(nb_a, 'tfd.MultivariateNormalDiag(tf.zeros(5), tf.ones(5)),\n    tfb.Exp())')
+  more['exp_normal_2x5_key_0'] = {'source': nb_a, 'cell': cell,
+                                  'value': np.asarray(fl(txt)[:10]).reshape(2, 5).tolist()}
+  nb_b = 'tensorflow_probability/examples/jupyter_notebooks/Distributed_Inference_with_JAX.ipynb'
+  cell, txt = notebook_output(nb_b, 'dist = tfd.Sample(tfd.Normal(0., 1.), jax.device_count())')
+  more['normal_8_key_0_tpu'] = {'source': nb_b, 'cell': cell, 'value': fl(txt.replace('float32', ''))[:8],
+                                'note': 'run on 8 TPU cores: the erfinv of that platform differs from the CPU one in '
+                                        'the last digits (the same three notebooks print normal(PRNGKey(0)) as '
+                                        '-0.20584226, -0.20584235 and -0.20584236)'}
+  rng['more'] = more
   json.dump(rng, open(os.path.join(HERE, 'jax_notebook_rng.json'), 'w'), indent=1)
   print('golden fixtures written to', HERE)
 

@@ -74,6 +74,13 @@ def test_rng_known_answers(tfp):
   draw = lambda kk: float(tfp.random.normal((1,), seed=kk, device=dev(), layout=1).cpu().numpy()[0])
   np.testing.assert_allclose(draw(orng.key(0)), g['normal_key_0'], rtol=2e-7)
   np.testing.assert_allclose([draw(kids[0]), draw(kids[1])], g['normal_split_keys'], rtol=2e-7)
+  m = g['more']
+  u = tfp.random.uniform((1, 2), seed=orng.key(0), device=dev(), layout=1).cpu().numpy()
+  np.testing.assert_allclose(u, [m['uniform_1x2_key_0']['value']], rtol=2e-7)
+  z = tfp.random.normal((2, 5), seed=orng.key(0), device=dev(), layout=1).cpu().numpy()
+  np.testing.assert_allclose(np.exp(z), m['exp_normal_2x5_key_0']['value'], rtol=1e-6)
+  z8 = tfp.random.normal((8,), seed=orng.key(0), device=dev(), layout=1).cpu().numpy()
+  np.testing.assert_allclose(z8, m['normal_8_key_0_tpu']['value'], rtol=2e-5)      # TPU erfinv: last digits
 
 
 def test_rng_2d_shape_row_major(tfp):

@@ -46,6 +46,13 @@ def test_rng_reproduces_the_jax_outputs_the_reference_keeps():
   loc, var = g['split_normal_exp_mean_variance']        # Normal(normal(k1), exp(normal(k2))): mean, variance
   np.testing.assert_allclose(z[0], loc, rtol=2e-7)
   np.testing.assert_allclose(np.exp(np.float32(z[1])) ** 2, var, rtol=1e-6)
+  # multi-element streams and a 2-d shape (the counter layout of the original generator), from two more notebooks
+  m = g['more']
+  np.testing.assert_allclose(orng.uniform(k, (2,), layout=orng.ORIGINAL), m['uniform_1x2_key_0']['value'], rtol=2e-7)
+  np.testing.assert_allclose(np.exp(orng.normal(k, (10,), orng.ORIGINAL)).reshape(2, 5),
+                             m['exp_normal_2x5_key_0']['value'], rtol=5e-7)
+  # a TPU run: same bits, that platform's erfinv (last digits differ; see the note in the fixture)
+  np.testing.assert_allclose(orng.normal(k, (8,), orng.ORIGINAL), m['normal_8_key_0_tpu']['value'], rtol=2e-5)
 
 
 def test_sample_chain_salt():
