@@ -36,7 +36,11 @@ PINNING STATUS
     partitionable layout has no reference-held vector (JAX-documented values
     only), and neither jax nor tensorflow is installable here.
   * HMC/NUTS transitions: the reference cannot be executed in this image
-    (needs tensorflow or jax); pinned only through the reference's
-    statistical/invariant tests restated in tests/.  "parity unpinned" for
-    bit-level trajectories.
+    (needs tensorflow or jax).  One reference-held RUN exists and is reproduced
+    (tests/golden/tf_notebook_hmc.json: the executed sample_chain cell of
+    TFP_Release_Notebook_0_11_0.ipynb, whose dynamics do not depend on the
+    generator: leapfrog, accept step and burn-in indexing); beyond it the
+    transitions are pinned through the reference's statistical / invariant tests
+    restated in tests/.  "parity unpinned" for bit-level trajectories of a
+    generator-dependent run.
 """

@@ -14,6 +14,9 @@ S&P 500 series are plain NumPy/Python files, importable without tensorflow/jax:
                                        both split keys, tfd.Normal(0, 1).sample(seed=PRNGKey(0)), and a jitted
                                        split -> normal -> exp chain) -- the reference-held pin of the threefry stream,
                                        the key split and the uniform -> normal transform of the seed contract (R1)
+  tf_notebook_hmc.json              <- the executed HMC cell of .../jupyter_notebooks/TFP_Release_Notebook_0_11_0.ipynb:
+                                       all_states / kernel results of a sample_chain run whose dynamics do not depend
+                                       on the generator (pins leapfrog + accept + burn-in indexing on a reference run)
 """
 import importlib.util
 import json
@@ -75,7 +78,7 @@ def main():
         return i, ' '.join(outs)
     raise KeyError(fragment)
 
-  num = r'-?\d+\.?\d*(?:e-?\d+)?'
+  num = r'-?\d+\.?\d*(?:e[+-]?\d+)?'
   fl = lambda txt: [float(v) for v in re.findall(num, txt)]
   rng = {'source': nb_path, 'cells': {}}
   for name, frag, parse in [
@@ -118,6 +121,20 @@ def main():
                                         'the last digits (the same three notebooks print normal(PRNGKey(0)) as '
                                         '-0.20584226, -0.20584235 and -0.20584236)'}
   rng['more'] = more
+  # ---- a reference-held HMC run (TF substrate, eager): sample_chain(num_results=5, num_burnin_steps=100) of
+  # HamiltonianMonteCarlo(lambda x: -(x - .2)**2, step_size=1., num_leapfrog_steps=2) from zeros([3]).  For this
+  # target two unit leapfrog steps map x -> 0.4 - x and m -> -m whatever the momentum, so the trajectory does not
+  # depend on the generator: it pins the leapfrog arithmetic, the accept step and sample_chain's burn-in indexing.
+  nb_c = 'tensorflow_probability/examples/jupyter_notebooks/TFP_Release_Notebook_0_11_0.ipynb'
+  cell, txt = notebook_output(nb_c, 'kernel = tfp.mcmc.HamiltonianMonteCarlo(lambda x: -(x - .2)**2')
+  first = txt[:txt.index('And again')]
+  blocks = re.findall(r'array\(\[\[(.*?)\]\]', first, re.S)
+  rows = lambda blk: [[float(v) for v in re.findall(num, r)] for r in blk.split('],')]
+  hmc = {'source': nb_c, 'cell': cell, 'step_size': 1.0, 'num_leapfrog_steps': 2, 'num_results': 5,
+         'num_burnin_steps': 100, 'all_states': rows(blocks[0]), 'log_acceptance_correction': rows(blocks[1])}
+  tl = re.search(r'target_log_prob=.*?array\(\[\[(.*?)\]', first, re.S).group(1)
+  hmc['target_log_prob_first_result'] = [float(v) for v in re.findall(num, tl)]
+  json.dump(hmc, open(os.path.join(HERE, 'tf_notebook_hmc.json'), 'w'), indent=1)
   json.dump(rng, open(os.path.join(HERE, 'jax_notebook_rng.json'), 'w'), indent=1)
   print('golden fixtures written to', HERE)
 

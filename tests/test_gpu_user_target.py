@@ -4,6 +4,8 @@ chain kernels.  Checked against the oracle: Eight Schools re-written by a "user"
 (log-prob / gradient to float32 rounding, the same HMC decisions and NUTS trees), a dense Gaussian handed over through
 `data` samples the right moments under sample_chain + dual averaging, multi-element-per-lane (D = 40) and cooperative
 (all 32 lanes) sources work."""
+import os
+
 import numpy as np
 import pytest
 
@@ -247,3 +249,31 @@ def test_user_target_behind_bijectors(tfp):
   n_eff = B * 150 / 4.0
   assert np.all(np.abs(s.mean(0) - mean) < 5 * np.sqrt(var / n_eff))
   np.testing.assert_allclose(s.var(0), var, rtol=0.05)
+
+
+QUADRATIC_SRC = r'''
+__device__ float target_log_prob_and_grad(const float* x, float* g, const float* data, int n_data) {
+  const float y = x[0] - 0.2f;
+  g[0] = -2.0f * y;
+  return -y * y;
+}
+'''
+
+
+def test_hmc_run_held_by_the_reference_notebook(tfp):
+  """tests/golden/tf_notebook_hmc.json (TFP_Release_Notebook_0_11_0.ipynb, executed cell 36): the reference's own
+  sample_chain(5, zeros([3]), HamiltonianMonteCarlo(lambda x: -(x - .2)**2, step_size=1., num_leapfrog_steps=2),
+  num_burnin_steps=100, seed=(1, 2)) run.  Two unit leapfrogs map x -> 0.4 - x, m -> -m for any momentum, so the
+  trajectory does not depend on the generator: the CUDA transitions (fused sample_chain over a run-time-compiled
+  target) reproduce the reference's printed states, log-probs and (vanishing) acceptance corrections."""
+  import json
+  g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'tf_notebook_hmc.json')))
+  tg = tfp.targets.UserTarget(1, QUADRATIC_SRC)
+  k = tfp.mcmc.HamiltonianMonteCarlo(tg, step_size=g['step_size'], num_leapfrog_steps=g['num_leapfrog_steps'])
+  r = tfp.mcmc.sample_chain(g['num_results'], torch.zeros(3, 1, device=dev()), kernel=k,
+                            num_burnin_steps=g['num_burnin_steps'], trace_fn=lambda _, kr: kr, seed=(1, 2))
+  np.testing.assert_allclose(r.all_states[:, :, 0].cpu().numpy(), g['all_states'], atol=1e-5)
+  assert bool(r.trace.is_accepted.all())
+  np.testing.assert_allclose(r.trace.accepted_results.target_log_prob[0].cpu().numpy(),
+                             g['target_log_prob_first_result'], atol=2e-6)
+  assert float(r.trace.accepted_results.log_acceptance_correction.abs().max()) < 2e-6

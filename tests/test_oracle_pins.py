@@ -55,6 +55,32 @@ def test_rng_reproduces_the_jax_outputs_the_reference_keeps():
   np.testing.assert_allclose(orng.normal(k, (8,), orng.ORIGINAL), m['normal_8_key_0_tpu']['value'], rtol=2e-5)
 
 
+def test_hmc_run_held_by_the_reference_notebook():
+  """tests/golden/tf_notebook_hmc.json: the executed cell of TFP_Release_Notebook_0_11_0.ipynb --
+  sample_chain(5, zeros([3]), HamiltonianMonteCarlo(lambda x: -(x - .2)**2, step_size=1., num_leapfrog_steps=2),
+  num_burnin_steps=100).  Two unit leapfrogs map x -> 0.4 - x, m -> -m for ANY momentum, so the run does not depend on
+  the generator: the oracle's leapfrog (leapfrog_integrator.py:222-316), accept step (metropolis_hastings.py:160-254)
+  and burn-in indexing (sample.py:311-383) reproduce the reference's printed states."""
+  import json, os
+  g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'tf_notebook_hmc.json')))
+
+  class Quadratic(object):
+    dim, part_sizes = 1, [1]
+
+    def logp_grad(self, x):
+      x = np.asarray(x, np.float32)
+      return (-(x[:, 0] - np.float32(0.2)) ** 2).astype(np.float32), (np.float32(-2.0) * (x - np.float32(0.2)))
+
+  states, trace, _ = omcmc.sample_chain(Quadratic(), 'hmc', np.zeros((3, 1), np.float32), g['num_results'],
+                                        num_burnin_steps=g['num_burnin_steps'], step_size=g['step_size'],
+                                        num_leapfrog_steps=g['num_leapfrog_steps'], seed=(1, 2))
+  np.testing.assert_allclose(states[:, :, 0], g['all_states'], atol=1e-5)
+  assert all(t['is_accepted'].all() for t in trace)
+  np.testing.assert_allclose(trace[0]['target_log_prob'], g['target_log_prob_first_result'], atol=2e-6)
+  assert max(np.abs(t['log_acceptance_correction']).max() for t in trace) < 2e-6
+  assert np.abs(np.asarray(g['log_acceptance_correction'])).max() < 2e-6
+
+
 def test_sample_chain_salt():
   # samplers.py:159-163 salt for 'mcmc.sample_chain' and the derived first step seed (SURVEY app. B)
   assert orng.salt_int('mcmc.sample_chain') == 1365385517
